@@ -1,0 +1,41 @@
+"""blp_b200 -- B200-native (sm_100a) scoring / loss / ranking hot path of dfdazac/blp.
+
+Public surface (same names as the reference's models.py / utils.py):
+
+    transe_score, distmult_score, complex_score, simple_score   models.py:222-248
+    margin_loss, nll_loss, l2_regularization                    models.py:251-266
+    LinkPrediction(.compute_loss), InductiveLinkPrediction,
+    TransductiveLinkPrediction                                   models.py:7-93, 207-219
+    get_metrics                                                  utils.py:86-111
+    rank_sweep                                                   train.py:128-171 (fused)
+    patch(models, utils)                                         rebinds the path inside the reference's modules
+
+All computation runs in libblp_b200.so (blp_b200/csrc, C ABI in include/blp_b200.h).
+"""
+from . import _lib, ops  # noqa: F401
+from ._lib import BlpError  # noqa: F401
+from .evaluate import finalize, gather_rows, rank_sweep, shard_bounds  # noqa: F401
+from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPrediction,  # noqa: F401
+                     complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,
+                     margin_loss, nll_loss, simple_score, transe_score)
+from .utils import TripleFilterIndex, get_metrics, make_ent2idx  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def patch(models_module, utils_module=None):
+    """Rebind the hot path inside the reference's own modules.
+
+    After `import models, utils; blp_b200.patch(models, utils)` every reference model class
+    (BertEmbeddingsLP, BOW, DKRL, ...) built afterwards binds the CUDA score / loss functions
+    (models.py:16-24, 31-34), `compute_loss` is the fused kernel, and train.py's
+    `utils.get_metrics(...)` calls run on the GPU.  train.py itself is untouched.
+    """
+    from . import models as _m
+    for name in ("transe_score", "distmult_score", "complex_score", "simple_score",
+                 "margin_loss", "nll_loss", "l2_regularization"):
+        setattr(models_module, name, getattr(_m, name))
+    models_module.LinkPrediction.compute_loss = _m.compute_loss
+    if utils_module is not None:
+        utils_module.get_metrics = get_metrics
+    return models_module

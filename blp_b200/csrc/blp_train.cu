@@ -1,0 +1,441 @@
+// blp_train.cu -- fused LinkPrediction.compute_loss forward + backward (a5-a8).
+//
+// Replaces models.py:51-70 (rel lookup, positive scores, in-batch negative
+// gather `ent_embs.view(2B, D)[neg_idx]`, negative scores, margin / NLL loss,
+// optional L2 regulariser) and the autograd graph behind it with ONE kernel:
+// the (B, K, 2, D) gather, the (B, K, D) broadcast intermediates and the
+// (B, K) score matrix of the reference are never materialised (neg_scores is
+// written only because callers may ask for it).
+//
+// Mapping: CTA = (positive row b, slice of its K negatives); one warp scores a
+// negative with the dim axis spread over its lanes (coalesced 8-byte vector
+// loads of the two gathered rows, warp-shuffle reduction), keeps several
+// negatives in flight to cover L2 latency, and -- because the loss is linear in
+// the upstream gradient -- immediately accumulates d loss / d rows:
+//   * the positive rows (2b, 2b+1) and the relation row accumulate in registers
+//     and are flushed once per warp;
+//   * rows sampled as corrupting entities take vector reductions (red.global)
+//     into grad_ent.
+// The working set (2B rows, the int64 index tensor) is L2 resident; at B=64 the
+// whole step is launch-latency bound, which is why it is a single launch plus
+// one memset.  The scalar loss is reduced deterministically by the last CTA.
+#include "blp_common.cuh"
+
+namespace blp {
+
+constexpr int kTrainThreads = 512;
+constexpr int kTrainWarps = kTrainThreads / 32;
+
+struct TrainArgs {
+    const float *ent;          // [2b, d]
+    const float *rel_weight;   // [num_rel, d]
+    const long long *rels;     // [b]
+    const long long *neg_idx;  // strided (b, k, 2)
+    long long s0, s1, s2;
+    long long b, k, num_rel;
+    int d;
+    int slices;                // CTAs per positive row
+    int loss;
+    float regularizer;
+    float *loss_out;
+    float *pos_scores;
+    float *neg_scores;
+    float *grad_ent;
+    float *grad_rel;            // [num_rel, d], rows rels[b] accumulate
+    unsigned int *counter;     // workspace[0]
+    float *partials;           // workspace + 16 floats
+    int *err_flag;             // workspace[1]: set when an index is out of range
+};
+
+template <int MODEL>
+struct TM {
+    static constexpr bool kHalves = (MODEL == BLP_MODEL_COMPLEX || MODEL == BLP_MODEL_SIMPLE);
+};
+
+template <int NCH2>
+struct Row {
+    float2 lo[NCH2];
+    float2 hi[NCH2];
+};
+
+template <int MODEL, int NCH2>
+__device__ __forceinline__ void load_row(Row<NCH2> &x, const float *__restrict__ row, int P, int lane) {
+#pragma unroll
+    for (int c = 0; c < NCH2; ++c) {
+        const int p = 2 * lane + 64 * c;
+        x.lo[c] = make_float2(0.f, 0.f);
+        x.hi[c] = make_float2(0.f, 0.f);
+        if (p < P) {
+            x.lo[c] = *reinterpret_cast<const float2 *>(row + p);
+            if (TM<MODEL>::kHalves) x.hi[c] = *reinterpret_cast<const float2 *>(row + P + p);
+        }
+    }
+}
+
+template <int MODEL>
+__device__ __forceinline__ float term1(float hl, float hh, float tl, float th, float rl, float rh) {
+    if (MODEL == BLP_MODEL_TRANSE) return fabsf((hl + rl) - tl);
+    if (MODEL == BLP_MODEL_DISTMULT) return (hl * rl) * tl;
+    if (MODEL == BLP_MODEL_COMPLEX) return rl * hl * tl + rl * hh * th + rh * hl * th - rh * hh * tl;
+    return hl * rl * th + tl * rh * hh;
+}
+
+template <int MODEL, int NCH2>
+__device__ __forceinline__ float partial_score(const Row<NCH2> &h, const Row<NCH2> &t, const Row<NCH2> &r) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH2; ++c) {
+        s += term1<MODEL>(h.lo[c].x, h.hi[c].x, t.lo[c].x, t.hi[c].x, r.lo[c].x, r.hi[c].x);
+        s += term1<MODEL>(h.lo[c].y, h.hi[c].y, t.lo[c].y, t.hi[c].y, r.lo[c].y, r.hi[c].y);
+    }
+    return s;
+}
+
+template <int MODEL>
+__device__ __forceinline__ float finish_score(float s) {
+    if (MODEL == BLP_MODEL_TRANSE) return -s;
+    if (MODEL == BLP_MODEL_SIMPLE) return 0.5f * s;
+    return s;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// d score / d (h, t, r) at one position, scaled by w (SimplE's 1/2 folded into w by the caller)
+template <int MODEL>
+__device__ __forceinline__ void grad1(float w, float hl, float hh, float tl, float th, float rl, float rh,
+                                      float &dhl, float &dhh, float &dtl, float &dth, float &drl, float &drh) {
+    if (MODEL == BLP_MODEL_TRANSE) {
+        const float x = (hl + rl) - tl;
+        const float sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);   // sign(0) = 0, like torch
+        dhl = -w * sg; drl = -w * sg; dtl = w * sg;
+        dhh = dth = drh = 0.f;
+    } else if (MODEL == BLP_MODEL_DISTMULT) {
+        dhl = w * rl * tl; dtl = w * hl * rl; drl = w * hl * tl;
+        dhh = dth = drh = 0.f;
+    } else if (MODEL == BLP_MODEL_COMPLEX) {   // l = re, h = im
+        dhl = w * (rl * tl + rh * th);
+        dhh = w * (rl * th - rh * tl);
+        dtl = w * (rl * hl - rh * hh);
+        dth = w * (rl * hh + rh * hl);
+        drl = w * (hl * tl + hh * th);
+        drh = w * (hl * th - hh * tl);
+    } else {   // SIMPLE: heads = (hh_, ht_) = (hl, hh); tails = (th_, tt_) = (tl, th); rels = (ra, rb) = (rl, rh)
+        dhl = w * rl * th;
+        dhh = w * tl * rh;
+        dtl = w * rh * hh;
+        dth = w * hl * rl;
+        drl = w * hl * th;
+        drh = w * tl * hh;
+    }
+}
+
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int MODEL, int NCH2>
+struct Acc {
+    Row<NCH2> h, t, r;
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int c = 0; c < NCH2; ++c) {
+            h.lo[c] = h.hi[c] = t.lo[c] = t.hi[c] = r.lo[c] = r.hi[c] = make_float2(0.f, 0.f);
+        }
+    }
+};
+
+template <int MODEL, int NCH2>
+__device__ __forceinline__ void flush_row(float *__restrict__ dst, const Row<NCH2> &g, int P, int lane) {
+#pragma unroll
+    for (int c = 0; c < NCH2; ++c) {
+        const int p = 2 * lane + 64 * c;
+        if (p < P) {
+            red_add_v2(dst + p, g.lo[c].x, g.lo[c].y);
+            if (TM<MODEL>::kHalves) red_add_v2(dst + P + p, g.hi[c].x, g.hi[c].y);
+        }
+    }
+}
+
+// accumulate w * dscore into (gh, gt, gr); each may be a register accumulator
+template <int MODEL, int NCH2>
+__device__ __forceinline__ void accumulate(float w, const Row<NCH2> &h, const Row<NCH2> &t, const Row<NCH2> &r,
+                                           Row<NCH2> &gh, Row<NCH2> &gt, Row<NCH2> &gr) {
+#pragma unroll
+    for (int c = 0; c < NCH2; ++c) {
+        float a, b2, c2, d2, e, f;
+        grad1<MODEL>(w, h.lo[c].x, h.hi[c].x, t.lo[c].x, t.hi[c].x, r.lo[c].x, r.hi[c].x, a, b2, c2, d2, e, f);
+        gh.lo[c].x += a; gh.hi[c].x += b2; gt.lo[c].x += c2; gt.hi[c].x += d2; gr.lo[c].x += e; gr.hi[c].x += f;
+        grad1<MODEL>(w, h.lo[c].y, h.hi[c].y, t.lo[c].y, t.hi[c].y, r.lo[c].y, r.hi[c].y, a, b2, c2, d2, e, f);
+        gh.lo[c].y += a; gh.hi[c].y += b2; gt.lo[c].y += c2; gt.hi[c].y += d2; gr.lo[c].y += e; gr.hi[c].y += f;
+    }
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad_f(float x) {
+    if (x > 20.f) return 1.f;
+    const float z = expf(x);
+    return z / (z + 1.f);
+}
+
+template <int MODEL, int NCH2, int ILP, bool GRAD>
+__global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long b = blockIdx.x / a.slices;
+    const int slice = blockIdx.x % a.slices;
+    const int d = a.d;
+    const int P = TM<MODEL>::kHalves ? d / 2 : d;          // positions owned pairwise by the lanes
+    const float half = (MODEL == BLP_MODEL_SIMPLE) ? 0.5f : 1.0f;
+    const long long nb2 = 2 * a.b;
+
+    // positive triple of this row (models.py:55-57)
+    long long rel = a.rels[b];
+    if (rel < 0 || rel >= a.num_rel) {
+        if (threadIdx.x == 0) *a.err_flag = 1;
+        rel = 0;
+    }
+    Row<NCH2> hb, tb, rb;
+    load_row<MODEL, NCH2>(hb, a.ent + (2 * b) * d, P, lane);
+    load_row<MODEL, NCH2>(tb, a.ent + (2 * b + 1) * d, P, lane);
+    load_row<MODEL, NCH2>(rb, a.rel_weight + rel * d, P, lane);
+    const float pos = finish_score<MODEL>(warp_sum(partial_score<MODEL, NCH2>(hb, tb, rb)));
+    const float one_minus_pos = 1.0f - pos;
+
+    const float inv_bk = 1.0f / (float)(a.b * a.k);
+    Acc<MODEL, NCH2> acc;
+    if (GRAD) acc.zero();
+    float loss_part = 0.f;    // lane-uniform
+    float wsum = 0.f;         // sum of negative weights handled by this warp (margin: feeds d/dpos)
+
+    const long long kps = (a.k + a.slices - 1) / a.slices;
+    const long long kb = slice * kps;
+    const long long ke = min(a.k, kb + kps);
+    const long long *nrow = a.neg_idx + b * a.s0;
+
+    for (long long k0 = kb + (long long)warp * ILP; k0 < ke; k0 += (long long)kTrainWarps * ILP) {
+        long long i0[ILP], i1[ILP];
+        Row<NCH2> nh[ILP], nt[ILP];
+        float part[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const long long kk = k0 + u;
+            i0[u] = 0; i1[u] = 0;
+            if (kk < ke) {
+                i0[u] = nrow[kk * a.s1];
+                i1[u] = nrow[kk * a.s1 + a.s2];
+                if (i0[u] < 0 || i0[u] >= nb2 || i1[u] < 0 || i1[u] >= nb2) {
+                    if (lane == 0) *a.err_flag = 1;
+                    i0[u] = 2 * b; i1[u] = 2 * b + 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            load_row<MODEL, NCH2>(nh[u], a.ent + i0[u] * d, P, lane);
+            load_row<MODEL, NCH2>(nt[u], a.ent + i1[u] * d, P, lane);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) part[u] = partial_score<MODEL, NCH2>(nh[u], nt[u], rb);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const long long kk = k0 + u;
+            if (kk >= ke) continue;   // warp-uniform
+            const float sc = finish_score<MODEL>(part[u]);
+            if (a.neg_scores && lane == 0) a.neg_scores[b * a.k + kk] = sc;
+            float w;
+            if (a.loss == BLP_LOSS_MARGIN) {
+                // models.py:252-253: m = fl(fl(1 - pos) + neg); entries with m < 0 are zeroed (m == 0 keeps its gradient)
+                const float m = one_minus_pos + sc;
+                const bool keep = !(m < 0.f);
+                if (keep) loss_part += m;
+                w = keep ? inv_bk : 0.f;
+                wsum += w;
+            } else {
+                // models.py:258: softplus(neg).mean() / 2
+                loss_part += softplus_f(sc);
+                w = 0.5f * inv_bk * softplus_grad_f(sc);
+            }
+            if (GRAD && w != 0.f) {
+                const float ws = w * half;
+                const bool own_h = (i0[u] == 2 * b), own_t = (i1[u] == 2 * b + 1);   // warp-uniform
+                if (own_h && own_t) {
+                    accumulate<MODEL, NCH2>(ws, nh[u], nt[u], rb, acc.h, acc.t, acc.r);
+                } else if (own_h) {
+                    Row<NCH2> g;
+#pragma unroll
+                    for (int c = 0; c < NCH2; ++c) g.lo[c] = g.hi[c] = make_float2(0.f, 0.f);
+                    accumulate<MODEL, NCH2>(ws, nh[u], nt[u], rb, acc.h, g, acc.r);
+                    flush_row<MODEL, NCH2>(a.grad_ent + i1[u] * d, g, P, lane);
+                } else if (own_t) {
+                    Row<NCH2> g;
+#pragma unroll
+                    for (int c = 0; c < NCH2; ++c) g.lo[c] = g.hi[c] = make_float2(0.f, 0.f);
+                    accumulate<MODEL, NCH2>(ws, nh[u], nt[u], rb, g, acc.t, acc.r);
+                    flush_row<MODEL, NCH2>(a.grad_ent + i0[u] * d, g, P, lane);
+                } else {
+                    Row<NCH2> g0, g1;
+#pragma unroll
+                    for (int c = 0; c < NCH2; ++c) g0.lo[c] = g0.hi[c] = g1.lo[c] = g1.hi[c] = make_float2(0.f, 0.f);
+                    accumulate<MODEL, NCH2>(ws, nh[u], nt[u], rb, g0, g1, acc.r);
+                    flush_row<MODEL, NCH2>(a.grad_ent + i0[u] * d, g0, P, lane);
+                    flush_row<MODEL, NCH2>(a.grad_ent + i1[u] * d, g1, P, lane);
+                }
+            }
+        }
+    }
+
+    // positive-side gradient: margin d/dpos = -sum_k w_bk (each warp adds its share); nll: -sigmoid(-pos)/(2B)
+    const bool lead = (slice == 0 && warp == 0);
+    if (GRAD) {
+        float wpos = (a.loss == BLP_LOSS_MARGIN) ? -wsum : (lead ? -0.5f * softplus_grad_f(-pos) / (float)a.b : 0.f);
+        if (wpos != 0.f) accumulate<MODEL, NCH2>(wpos * half, hb, tb, rb, acc.h, acc.t, acc.r);
+        if (lead && a.regularizer > 0.f) {
+            // models.py:59-62, 261-266: d/dx of regularizer * mean(x^2) / 3
+            const float cr = a.regularizer * 2.0f / (3.0f * (float)a.b * (float)d);
+#pragma unroll
+            for (int c = 0; c < NCH2; ++c) {
+                acc.h.lo[c].x += cr * hb.lo[c].x; acc.h.lo[c].y += cr * hb.lo[c].y;
+                acc.t.lo[c].x += cr * tb.lo[c].x; acc.t.lo[c].y += cr * tb.lo[c].y;
+                acc.r.lo[c].x += cr * rb.lo[c].x; acc.r.lo[c].y += cr * rb.lo[c].y;
+                acc.h.hi[c].x += cr * hb.hi[c].x; acc.h.hi[c].y += cr * hb.hi[c].y;
+                acc.t.hi[c].x += cr * tb.hi[c].x; acc.t.hi[c].y += cr * tb.hi[c].y;
+                acc.r.hi[c].x += cr * rb.hi[c].x; acc.r.hi[c].y += cr * rb.hi[c].y;
+            }
+        }
+        flush_row<MODEL, NCH2>(a.grad_ent + (2 * b) * d, acc.h, P, lane);
+        flush_row<MODEL, NCH2>(a.grad_ent + (2 * b + 1) * d, acc.t, P, lane);
+        flush_row<MODEL, NCH2>(a.grad_rel + rel * d, acc.r, P, lane);
+    }
+
+    // ---- loss: per-CTA partial, deterministic final reduction by the last CTA
+    __shared__ float s_part[kTrainWarps];
+    __shared__ bool s_last;
+    float mine;
+    if (a.loss == BLP_LOSS_MARGIN) mine = loss_part * inv_bk;
+    else mine = loss_part * 0.5f * inv_bk;
+    if (lead) {
+        if (a.loss == BLP_LOSS_NLL) mine += 0.5f * softplus_f(-pos) / (float)a.b;
+        if (a.regularizer > 0.f) {
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH2; ++c) {
+                sq += hb.lo[c].x * hb.lo[c].x + hb.lo[c].y * hb.lo[c].y + hb.hi[c].x * hb.hi[c].x + hb.hi[c].y * hb.hi[c].y;
+                sq += tb.lo[c].x * tb.lo[c].x + tb.lo[c].y * tb.lo[c].y + tb.hi[c].x * tb.hi[c].x + tb.hi[c].y * tb.hi[c].y;
+                sq += rb.lo[c].x * rb.lo[c].x + rb.lo[c].y * rb.lo[c].y + rb.hi[c].x * rb.hi[c].x + rb.hi[c].y * rb.hi[c].y;
+            }
+            sq = warp_sum(sq);
+            mine += a.regularizer * sq / (3.0f * (float)a.b * (float)d);
+        }
+        if (lane == 0) a.pos_scores[b] = pos;
+    }
+    if (lane == 0) s_part[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < kTrainWarps; ++w) tot += s_part[w];
+        a.partials[blockIdx.x] = tot;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned int i = lane; i < gridDim.x; i += 32) tot += (double)__ldcg(a.partials + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) {
+            *a.loss_out = (float)tot;
+            *a.counter = 0u;   // leave the workspace zeroed for the next call
+        }
+    }
+}
+
+template <int MODEL, int NCH2, int ILP>
+static int launch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
+    const unsigned grid = (unsigned)(a.b * a.slices);
+    if (grad) train_kernel<MODEL, NCH2, ILP, true><<<grid, kTrainThreads, 0, st>>>(a);
+    else train_kernel<MODEL, NCH2, ILP, false><<<grid, kTrainThreads, 0, st>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "train_kernel launch");
+}
+
+template <int MODEL>
+static int dispatch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
+    const int P = TM<MODEL>::kHalves ? a.d / 2 : a.d;
+    const int need = (P + 63) / 64;
+    if (need <= 1) return launch_train<MODEL, 1, 4>(a, grad, st);
+    if (need <= 2) return launch_train<MODEL, 2, 4>(a, grad, st);
+    if (need <= 4) return launch_train<MODEL, 4, 2>(a, grad, st);
+    if (need <= 6) return launch_train<MODEL, 6, 2>(a, grad, st);
+    if (need <= 12) return launch_train<MODEL, 12, 1>(a, grad, st);
+    if (need <= 16) return launch_train<MODEL, 16, 1>(a, grad, st);
+    set_error("fused compute_loss supports d <= %d for this model (got %d)", TM<MODEL>::kHalves ? 2048 : 1024, a.d);
+    return BLP_EDIM;
+}
+
+}  // namespace blp
+
+using namespace blp;
+
+extern "C" int64_t blp_train_workspace_bytes(int64_t b, int64_t k) {
+    (void)k;
+    if (b < 0) return 0;
+    return 64 + 4 * b * 8;   // counter + error flag + one float partial per CTA (<= 8 slices per row)
+}
+
+extern "C" int blp_train_loss(int model, int loss, const float *ent_embs, const float *rel_weight, const int64_t *rels,
+                              int64_t num_rel, const int64_t *neg_idx, int64_t s0, int64_t s1, int64_t s2, int64_t b,
+                              int64_t k, int d, float regularizer, float *loss_out, float *pos_scores,
+                              float *neg_scores, float *grad_ent, float *grad_rel_weight, void *workspace, void *stream) {
+    reset_launch_count();
+    if (model < 0 || model > 3) { set_error("unknown relational model id %d", model); return BLP_EINVAL; }
+    if (loss != BLP_LOSS_MARGIN && loss != BLP_LOSS_NLL) { set_error("unknown loss id %d", loss); return BLP_EINVAL; }
+    if (b <= 0 || k <= 0 || num_rel <= 0) { set_error("b, k and num_rel must be positive"); return BLP_EINVAL; }
+    if (d <= 0 || (d & 1)) { set_error("fused compute_loss needs an even d (got %d)", d); return BLP_EDIM; }
+    if ((model == BLP_MODEL_COMPLEX || model == BLP_MODEL_SIMPLE) && (d & 3)) {
+        set_error("fused compute_loss needs d %% 4 == 0 for complex/simple (got %d)", d);
+        return BLP_EDIM;
+    }
+    if (!ent_embs || !rel_weight || !rels || !neg_idx || !loss_out || !pos_scores || !workspace) {
+        set_error("null pointer argument");
+        return BLP_EINVAL;
+    }
+    if ((grad_ent == nullptr) != (grad_rel_weight == nullptr)) { set_error("grad_ent and grad_rel_weight must both be given or both NULL"); return BLP_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(ent_embs) | reinterpret_cast<uintptr_t>(rel_weight)) & 7u) {
+        set_error("ent_embs / rel_weight must be 8-byte aligned");
+        return BLP_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool grad = grad_ent != nullptr;
+    if (grad) {
+        BLP_CUDA(cudaMemsetAsync(grad_ent, 0, sizeof(float) * (size_t)(2 * b) * d, st));
+        BLP_CUDA(cudaMemsetAsync(grad_rel_weight, 0, sizeof(float) * (size_t)num_rel * d, st));
+    }
+    TrainArgs a{};
+    a.ent = ent_embs; a.rel_weight = rel_weight; a.rels = (const long long *)rels; a.neg_idx = (const long long *)neg_idx;
+    a.s0 = s0; a.s1 = s1; a.s2 = s2; a.b = b; a.k = k; a.num_rel = num_rel; a.d = d; a.loss = loss; a.regularizer = regularizer;
+    a.loss_out = loss_out; a.pos_scores = pos_scores; a.neg_scores = neg_scores; a.grad_ent = grad_ent; a.grad_rel = grad_rel_weight;
+    a.counter = reinterpret_cast<unsigned int *>(workspace);
+    a.err_flag = reinterpret_cast<int *>(workspace) + 1;
+    a.partials = reinterpret_cast<float *>(workspace) + 16;
+    // enough CTAs to cover the SMs about twice, at least one 16-warp pass of negatives per CTA
+    int slices = 1;
+    while (slices < 8 && b * slices < 296 && k / (slices * 2) >= kTrainWarps * 2) slices *= 2;
+    a.slices = slices;
+    switch (model) {
+    case BLP_MODEL_TRANSE: return dispatch_train<BLP_MODEL_TRANSE>(a, grad, st);
+    case BLP_MODEL_DISTMULT: return dispatch_train<BLP_MODEL_DISTMULT>(a, grad, st);
+    case BLP_MODEL_COMPLEX: return dispatch_train<BLP_MODEL_COMPLEX>(a, grad, st);
+    default: return dispatch_train<BLP_MODEL_SIMPLE>(a, grad, st);
+    }
+}

@@ -1,0 +1,159 @@
+"""Full-entity scoring + ranking sweep: the hot loop of eval_link_prediction (train.py:128-171).
+
+The reference scores a batch of B test triples against every candidate entity
+twice (all heads, all tails), materialises a (2B, N) score matrix, and turns it
+into ranks with utils.get_metrics (raw, then again after masking filtered
+candidates).  Here a whole sweep is one or a few `blp_eval_rank` launches that
+read the entity table once per query group and emit two integer counters per
+query; reciprocal ranks / hits@k are computed once at the end.
+
+Multi-GPU: the candidate axis is sharded by rows; each
+rank counts over its shard and ONE all-reduce of the int32 counters per sweep
+merges them.  Integer sums are exact, so the result is identical for any world
+size.  The query rows (true head / tail rows) are exchanged once per sweep with
+a bit-preserving all-reduce (every row is owned by exactly one rank).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+K_VALUES = (1, 3, 10)          # train.py:66 hit_positions
+
+
+def shard_bounds(n, world_size, rank):
+    """Row block owned by `rank`: [lo, hi) with blocks of ceil(n / world_size) rows."""
+    per = -(-int(n) // int(world_size))
+    lo = min(int(n), rank * per)
+    return lo, min(int(n), lo + per)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _world(group):
+    dist = _dist()
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def gather_rows(ent_shard, ent_offset, idx, group=None):
+    """Rows `idx` (global ids) of a row-sharded table, replicated on every rank (train.py:141-142).
+
+    Each row lives on exactly one rank; the others contribute zero bit patterns, and the sum is taken
+    on the int32 view, so the result is the owner's bits exactly (including signed zeros).
+    """
+    world, _ = _world(group)
+    idx = idx.reshape(-1)
+    if world == 1:
+        return ent_shard.index_select(0, idx - ent_offset if ent_offset else idx)
+    local = idx - ent_offset
+    mine = (local >= 0) & (local < ent_shard.shape[0])
+    rows = torch.zeros((idx.numel(), ent_shard.shape[1]), dtype=ent_shard.dtype, device=ent_shard.device)
+    sel = mine.nonzero().reshape(-1)
+    rows.index_copy_(0, sel, ent_shard.index_select(0, local.index_select(0, sel)))
+    _dist().all_reduce(rows.view(torch.int32), group=group)
+    return rows
+
+
+def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, filter_triples=None,
+               filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384,
+               h_rows=None, t_rows=None, count_fn=None):
+    """Rank every test triple against all candidate entities (train.py:128-171 for the whole sweep).
+
+    rel_model   'transe' | 'distmult' | 'complex' | 'simple'
+    ent_emb     (N_local, D) fp32: this rank's row shard of the entity table (the whole table when
+                not distributed); row j is candidate `ent_offset + j`
+    rel_weight  (R, D) relation table (model.rel_emb.weight)
+    triples     (T, 3) int64 (head_row, tail_row, rel_id): table ROWS, i.e. after ent2idx (train.py:132-135)
+    filter_index / filter_triples   a utils.TripleFilterIndex and the (T, 3) entity-ID triples for the
+                filtered setting (train.py:159-167); or filter_csr = (indptr [2T+1], idx) precomputed with
+                the head-prediction queries of ALL T triples first
+    h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
+    count_fn    test seam: replaces ops.eval_rank (same signature) so the sharding / collective logic can
+                be exercised without a GPU
+
+    Returns a dict: gt, ge (and gt_f, ge_f) int32 (2, T) [0 = head prediction, 1 = tail prediction],
+    recip / hits (and recip_f / hits_f) per query, `sums` float64 [sum 1/rank, hits@k...] (and sums_f),
+    mrr / hits_at_k (and mrr_f / hits_at_k_f) python floats normalised by 2T (train.py:196-200).
+    """
+    count = count_fn or ops.eval_rank
+    dev = ent_emb.device
+    triples = triples.to(dev).reshape(-1, 3)
+    T = triples.shape[0]
+    heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
+    world, _ = _world(group)
+    filtered = filter_index is not None or filter_csr is not None
+
+    if h_rows is None:
+        h_rows = gather_rows(ent_emb, ent_offset, heads, group)
+    if t_rows is None:
+        t_rows = gather_rows(ent_emb, ent_offset, tails, group)
+    r_rows = rel_weight.detach().index_select(0, rels)                      # train.py:143 rel_emb lookup
+
+    names = ("gt", "ge", "gt_f", "ge_f") if filtered else ("gt", "ge")
+    counters = torch.zeros((len(names), 2, T), dtype=torch.int32, device=dev)
+    true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
+    launches = 0
+    for lo in range(0, T, chunk):
+        hi = min(T, lo + chunk)
+        indptr = idx = None
+        if filtered:
+            if filter_csr is not None:
+                indptr, idx = _slice_csr(filter_csr, lo, hi, T)
+            else:
+                indptr, idx = filter_index.csr(filter_triples[lo:hi])
+            indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev, non_blocking=True)
+            idx = torch.as_tensor(idx if len(idx) else np.zeros(1, np.int64), dtype=torch.int64).to(dev, non_blocking=True)
+        res = count(rel_model, ent_emb, h_rows[lo:hi], t_rows[lo:hi], r_rows[lo:hi], indptr, idx, ent_offset)
+        b = hi - lo
+        for i, name in enumerate(names):
+            counters[i, 0, lo:hi] = res[name][:b]
+            counters[i, 1, lo:hi] = res[name][b:]
+        true_score[0, lo:hi] = res["true_score"][:b]
+        true_score[1, lo:hi] = res["true_score"][b:]
+        launches += res.get("launches", 0)
+
+    if world > 1:
+        _dist().all_reduce(counters, group=group)                           # the one collective of the sweep
+
+    out = {name: counters[i] for i, name in enumerate(names)}
+    out["true_score"] = true_score
+    out["launches"] = launches
+    if count_fn is None:
+        for suffix in ("", "_f") if filtered else ("",):
+            gt, ge = out["gt" + suffix].reshape(-1), out["ge" + suffix].reshape(-1)
+            recip, hits = ops.metrics_from_counts(gt, ge, k_values)
+            sums = ops.metrics_reduce(gt, ge, k_values)
+            out["recip" + suffix], out["hits" + suffix], out["sums" + suffix] = recip, hits, sums
+            out["launches"] += 2
+    return out
+
+
+def finalize(out, num_queries=None):
+    """Host-side normalisation (train.py:196-200): one D2H read of the fp64 accumulators per sweep."""
+    res = {}
+    for suffix in ("", "_f"):
+        if "sums" + suffix not in out:
+            continue
+        sums = out["sums" + suffix].tolist()
+        q = num_queries or out["gt"].numel()
+        res["mrr" + suffix] = sums[0] / q
+        res["hits_at_k" + suffix] = [s / q for s in sums[1:]]
+    return res
+
+
+def _slice_csr(csr, lo, hi, T):
+    """Sub-CSR for triples [lo, hi): head-prediction rows lo..hi of the first T rows, then the tail rows."""
+    indptr, idx = (np.asarray(a, dtype=np.int64) for a in csr)
+    parts, lens = [], []
+    for base in (0, T):
+        s, e = indptr[base + lo], indptr[base + hi]
+        parts.append(idx[s:e])
+        lens.append(np.diff(indptr[base + lo:base + hi + 1]))
+    sub = np.zeros(2 * (hi - lo) + 1, np.int64)
+    np.cumsum(np.concatenate(lens), out=sub[1:])
+    return sub, np.concatenate(parts)

@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C ABI (include/blp_b200.h).
+
+PyTorch is plumbing here: it owns the device memory and the stream; every
+computation is a call into libblp_b200.so.  Nothing in this module computes a
+score, a loss or a rank with torch ops, and nothing falls back to the CPU.
+"""
+import ctypes
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import LOSSES, MODELS, check, lib
+
+
+def _require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.BlpError(
+                "blp_b200 runs on sm_100 CUDA tensors only (got a %s tensor); there is no CPU fallback" % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"tensors on different devices: {dev} and {t.device}")
+    return dev
+
+
+_checked_devices = set()
+
+
+def _enter(dev):
+    """Device guard + one-time architecture check; returns the current stream handle."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        check(lib().blp_device_check(idx), "blp_device_check")
+        _checked_devices.add(idx)
+    return idx, ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise ValueError(f"blp_b200 kernels are fp32 only (got {t.dtype})")
+    return t.contiguous()
+
+
+def model_id(name):
+    try:
+        return MODELS[name]
+    except KeyError:
+        raise ValueError(f"Unknown relational model {name}.") from None      # models.py:26
+
+
+def loss_id(name):
+    try:
+        return LOSSES[name]
+    except KeyError:
+        raise ValueError(f"Unkown loss function {name}") from None           # models.py:36 (sic)
+
+
+# ---------------------------------------------------------------- score_fn ----
+def _as_acd(x, lead, d):
+    """View operand x (broadcastable to lead + (d,)) as rows addressed by (a, c) element strides."""
+    x = _f32c(x)
+    if x.shape[-1] != d:
+        raise ValueError(f"last dim mismatch: {tuple(x.shape)} vs d={d}")
+    xl = (1,) * (len(lead) - (x.dim() - 1)) + tuple(x.shape[:-1])
+    x = x.reshape(xl + (d,))
+    return x, xl
+
+
+def score(model, heads, tails, rels):
+    """score_fn(heads, tails, rels) (models.py:222-248): broadcast leading dims, reduce the last.
+
+    Forward only (the differentiable training path is `compute_loss`).  Operands must broadcast
+    to at most two distinct leading axes, which covers every call site of the reference
+    (train.py:146-147, models.py:57,67).
+    """
+    mid = model_id(model)
+    if any(t.requires_grad for t in (heads, tails, rels)) and torch.is_grad_enabled():
+        raise _lib.BlpError("blp_b200 score functions are forward-only; train through LinkPrediction.compute_loss")
+    dev = _require_cuda(heads, tails, rels)
+    d = heads.shape[-1]
+    lead = torch.broadcast_shapes(heads.shape[:-1], tails.shape[:-1], rels.shape[:-1])
+    ops, shapes = zip(*[_as_acd(x, lead, d) for x in (heads, tails, rels)])
+    # collapse the broadcast lead shape to (A, C): axes [0, split) -> A, [split, nd) -> C, such that
+    # every operand is either full or broadcast (all ones) on each of the two axis groups
+    nd = len(lead)
+
+    def _prod(seq):
+        out = 1
+        for v in seq:
+            out *= v
+        return out
+
+    def _fits(sh, s):
+        return all(tuple(seg) == tuple(ref) or all(v == 1 for v in seg)
+                   for seg, ref in ((sh[:s], lead[:s]), (sh[s:], lead[s:])))
+
+    split = next((s for s in range(nd + 1) if all(_fits(sh, s) for sh in shapes)), None)
+    if split is None:
+        raise NotImplementedError(f"broadcast pattern not supported by blp_score_bcast: {shapes}")
+    A, C = _prod(lead[:split]), _prod(lead[split:])
+    out = torch.empty((A, C), dtype=torch.float32, device=dev)
+    args = []
+    for x, sh in zip(ops, shapes):
+        a_full = tuple(sh[:split]) == tuple(lead[:split])
+        c_full = tuple(sh[split:]) == tuple(lead[split:])
+        sA = _prod(sh[split:]) * d if (a_full and A > 1) else 0
+        sC = d if (c_full and C > 1) else 0
+        args += [_ptr(x), sA, sC]
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        if A * C > 0:
+            check(lib().blp_score_bcast(mid, *args, A, C, d, _ptr(out), stream), "blp_score_bcast")
+    return out.reshape(lead)
+
+
+# ------------------------------------------------------------- get_metrics ----
+def rank_counts(pred_scores, true_idx):
+    """Integer part of utils.get_metrics (utils.py:103-105) -> (gt, ge) int32 (Q,)."""
+    dev = _require_cuda(pred_scores, true_idx)
+    if pred_scores.dim() != 2:
+        raise ValueError("pred_scores must be (Q, N)")
+    pred = pred_scores if (pred_scores.dtype == torch.float32 and pred_scores.stride(1) == 1) else _f32c(pred_scores)
+    q, n = pred.shape
+    ti = true_idx.reshape(-1).to(torch.int64).contiguous()
+    if ti.numel() != q:
+        raise ValueError("true_idx must have one entry per row of pred_scores")
+    gt = torch.empty(q, dtype=torch.int32, device=dev)
+    ge = torch.empty(q, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_rank_counts(_ptr(pred), q, n, pred.stride(0) if q > 1 else n, _ptr(ti), _ptr(gt), _ptr(ge), stream),
+              "blp_rank_counts")
+    return gt, ge
+
+
+def metrics_from_counts(gt, ge, k_values):
+    """Float part of utils.get_metrics (utils.py:106-109) -> (reciprocals (Q,1) f32, hits (Q,k) bool)."""
+    dev = _require_cuda(gt, ge)
+    ks = [int(v) for v in (k_values.reshape(-1).tolist() if torch.is_tensor(k_values) else k_values)]
+    q = gt.numel()
+    recip = torch.empty((q, 1), dtype=torch.float32, device=dev)
+    hits = torch.empty((q, len(ks)), dtype=torch.uint8, device=dev)
+    karr = (ctypes.c_int64 * max(1, len(ks)))(*ks)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_metrics_from_counts(_ptr(gt.contiguous()), _ptr(ge.contiguous()), q, karr, len(ks),
+                                            _ptr(recip), _ptr(hits), stream), "blp_metrics_from_counts")
+    return recip, hits.view(torch.bool)
+
+
+def metrics_reduce(gt, ge, k_values):
+    """train.py:154-157 accumulators -> float64 device tensor [sum 1/rank, hits@k_0, hits@k_1, ...]."""
+    dev = _require_cuda(gt, ge)
+    ks = [int(v) for v in (k_values.reshape(-1).tolist() if torch.is_tensor(k_values) else k_values)]
+    sums = torch.empty(1 + len(ks), dtype=torch.float64, device=dev)
+    karr = (ctypes.c_int64 * max(1, len(ks)))(*ks)
+    gt, ge = gt.reshape(-1).contiguous(), ge.reshape(-1).contiguous()
+    if gt.dtype != torch.int32 or ge.dtype != torch.int32:
+        raise ValueError("rank counters must be int32")
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_metrics_reduce(_ptr(gt), _ptr(ge), gt.numel(), karr, len(ks), _ptr(sums), stream),
+              "blp_metrics_reduce")
+    return sums
+
+
+# --------------------------------------------------------- fused eval sweep ----
+def eval_rank(model, ent, h_rows, t_rows, r_rows, filt_indptr=None, filt_idx=None, ent_offset=0):
+    """train.py:141-171 for one batch (or many) without the (2B, N) score matrix.
+
+    Returns dict(gt, ge[, gt_f, ge_f], true_score): int32 counts over THIS shard of the table for
+    the 2B queries (head predictions then tail predictions, the reference's cat order).
+    """
+    mid = model_id(model)
+    dev = _require_cuda(ent, h_rows, t_rows, r_rows, filt_indptr, filt_idx)
+    ent, h_rows, t_rows, r_rows = (_f32c(x) for x in (ent, h_rows, t_rows, r_rows))
+    if ent.dim() != 2:
+        raise ValueError("ent must be (N, D)")
+    n, d = ent.shape
+    b = h_rows.shape[0]
+    for x in (h_rows, t_rows, r_rows):
+        if x.shape != (b, d):
+            raise ValueError(f"query rows must be ({b}, {d}); got {tuple(x.shape)}")
+    gt = torch.empty(2 * b, dtype=torch.int32, device=dev)
+    ge = torch.empty(2 * b, dtype=torch.int32, device=dev)
+    ts = torch.empty(2 * b, dtype=torch.float32, device=dev)
+    out = {"gt": gt, "ge": ge, "true_score": ts}
+    gtf = gef = None
+    if filt_indptr is not None:
+        filt_indptr = filt_indptr.to(torch.int64).contiguous()
+        filt_idx = filt_idx.to(torch.int64).contiguous()
+        if filt_indptr.numel() != 2 * b + 1:
+            raise ValueError("filt_indptr must have 2B+1 entries")
+        gtf = torch.empty(2 * b, dtype=torch.int32, device=dev)
+        gef = torch.empty(2 * b, dtype=torch.int32, device=dev)
+        out["gt_f"], out["ge_f"] = gtf, gef
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_eval_rank(mid, _ptr(ent), n, int(ent_offset), d, _ptr(h_rows), _ptr(t_rows), _ptr(r_rows), b,
+                                  _ptr(filt_indptr), _ptr(filt_idx), _ptr(gt), _ptr(ge), _ptr(gtf), _ptr(gef),
+                                  _ptr(ts), stream), "blp_eval_rank")
+    out["launches"] = _lib.last_launch_count()
+    return out
+
+
+# ------------------------------------------------------ fused compute_loss ----
+_ws_lock = threading.Lock()
+_workspaces = {}
+
+
+def _workspace(dev_idx, stream_handle, nbytes):
+    """Zero-filled scratch, one per (device, stream): the kernel leaves it zeroed (blp_b200.h)."""
+    key = (dev_idx, stream_handle)
+    with _ws_lock:
+        ws = _workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=torch.device("cuda", dev_idx))
+            _workspaces[key] = ws
+    return ws
+
+
+def train_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=0.0, want_grad=True,
+               want_neg_scores=False):
+    """models.py:51-70 forward (+ analytic backward for an upstream gradient of 1) in one launch."""
+    mid, lid = model_id(model), loss_id(loss)
+    dev = _require_cuda(ent_embs, rel_weight, rels, neg_idx)
+    ent_embs, rel_weight = _f32c(ent_embs), _f32c(rel_weight)
+    if ent_embs.dim() != 3 or ent_embs.shape[1] != 2:
+        raise ValueError("ent_embs must be (B, 2, D)")
+    b, _, d = ent_embs.shape
+    rels = rels.reshape(-1).to(torch.int64).contiguous()
+    if rels.numel() != b:
+        raise ValueError("rels must have B entries")
+    if neg_idx.dtype != torch.int64 or neg_idx.dim() != 3 or neg_idx.shape[0] != b or neg_idx.shape[2] != 2:
+        raise ValueError("neg_idx must be an int64 (B, K, 2) tensor")
+    k = neg_idx.shape[1]
+    s0, s1, s2 = neg_idx.stride()
+    loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    pos = torch.empty(b, dtype=torch.float32, device=dev)
+    neg = torch.empty((b, k), dtype=torch.float32, device=dev) if want_neg_scores else None
+    g_ent = torch.empty((b, 2, d), dtype=torch.float32, device=dev) if want_grad else None
+    g_rel = torch.empty_like(rel_weight) if want_grad else None
+    with torch.cuda.device(dev):
+        idx, stream = _enter(dev)
+        ws = _workspace(idx, stream.value, int(lib().blp_train_workspace_bytes(b, k)))
+        check(lib().blp_train_loss(mid, lid, _ptr(ent_embs), _ptr(rel_weight), _ptr(rels), rel_weight.shape[0],
+                                   _ptr(neg_idx), s0, s1, s2, b, k, d, float(regularizer), _ptr(loss_out), _ptr(pos),
+                                   _ptr(neg), _ptr(g_ent), _ptr(g_rel), _ptr(ws), stream), "blp_train_loss")
+    return {"loss": loss_out, "pos_scores": pos, "neg_scores": neg, "grad_ent": g_ent, "grad_rel_weight": g_rel,
+            "launches": _lib.last_launch_count(), "workspace": ws}
+
+
+def scaled(x, scale_dev):
+    """x * scale_dev (device scalar) into a new tensor; the backward of the fused loss."""
+    dev = _require_cuda(x, scale_dev)
+    x = _f32c(x)
+    scale_dev = _f32c(scale_dev.reshape(1))
+    y = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_scale(_ptr(y), _ptr(x), _ptr(scale_dev), x.numel(), stream), "blp_scale")
+    return y
+
+
+def pair_loss(loss, pos_scores, neg_scores, want_grad=False):
+    """loss_fn(pos_scores (B,1), neg_scores (B,K)) (models.py:251-258) -> dict(loss[, grad_pos, grad_neg])."""
+    lid = loss_id(loss)
+    dev = _require_cuda(pos_scores, neg_scores)
+    if neg_scores.dim() != 2:
+        raise ValueError("neg_scores must be (B, K)")
+    b, k = neg_scores.shape
+    pos = _f32c(pos_scores).reshape(-1)
+    if pos.numel() != b:
+        raise ValueError("pos_scores must be (B, 1)")
+    neg = neg_scores if (neg_scores.dtype == torch.float32 and neg_scores.stride(1) == 1 and neg_scores.stride(0) >= k) \
+        else _f32c(neg_scores)
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    gp = torch.empty(b, dtype=torch.float32, device=dev) if want_grad else None
+    gn = torch.empty((b, k), dtype=torch.float32, device=dev) if want_grad else None
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_pair_loss(lid, _ptr(pos), _ptr(neg), neg.stride(0) if b > 1 else k, b, k, _ptr(out), _ptr(gp),
+                                  _ptr(gn), stream), "blp_pair_loss")
+    return {"loss": out, "grad_pos": gp, "grad_neg": gn}
+
+
+def l2_regularization(heads, tails, rels):
+    """models.py:261-266, forward only."""
+    dev = _require_cuda(heads, tails, rels)
+    heads, tails, rels = (_f32c(x) for x in (heads, tails, rels))
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_l2_regularization(_ptr(heads), heads.numel(), _ptr(tails), tails.numel(), _ptr(rels),
+                                          rels.numel(), _ptr(out), stream), "blp_l2_regularization")
+    return out.reshape(())
+
+
+def index_error_flag(result):
+    """True if the last train_loss call on that workspace saw an out-of-range rels / neg_idx entry (syncs)."""
+    flag = result["workspace"][4:8].view(torch.int32)
+    bad = bool(flag.item())
+    if bad:
+        flag.zero_()
+    return bad
+
+
+def pipe_probe(variant, device, n_threads=148 * 8 * 256, iters=4096):
+    """Launch one FP32 pipe micro-benchmark; returns the lane-op count (time it with CUDA events)."""
+    dev = torch.device(device)
+    sink = torch.empty(n_threads, dtype=torch.float32, device=dev)
+    ops = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_pipe_probe(int(variant), _ptr(sink), n_threads, iters, ctypes.byref(ops), stream), "blp_pipe_probe")
+    return ops.value, sink

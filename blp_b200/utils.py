@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's utils.py pieces on the ranking path.
+
+`get_metrics` (utils.py:86-111) runs as two kernels of libblp_b200.so; the
+filter helpers restate utils.py:31-83 as a one-off CSR build (the reference
+rebuilds a dense (B, N) bool mask per batch with Python loops over graph edges).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def get_metrics(pred_scores, true_idx, k_values):
+    """utils.py:86-111: (reciprocals (Q,1) f32, hits (Q,k) bool) from a (Q,N) score matrix."""
+    gt, ge = ops.rank_counts(pred_scores, true_idx)
+    return ops.metrics_from_counts(gt, ge, k_values)
+
+
+def make_ent2idx(entities, max_ent_id):
+    """utils.py:31-43 (host-side index plumbing; -1 marks ids that are not candidates)."""
+    idx = torch.arange(entities.shape[0])
+    ent2idx = torch.empty(max_ent_id + 1, dtype=torch.long).fill_(-1)
+    ent2idx.scatter_(0, entities.cpu(), idx)
+    return ent2idx
+
+
+class TripleFilterIndex:
+    """(head, rel) -> known tails and (tail, rel) -> known heads, built once per evaluation.
+
+    Restates utils.get_triple_filters (utils.py:46-83): for a test triple (h, t, r) the filtered
+    tail candidates are {t' : (h, t', r) in graph, t' != t} and the filtered head candidates are
+    {h' : (h', t, r) in graph, h' != h}, mapped through ent2idx and dropped when ent2idx is -1.
+    The reference emits a dense (B, N) bool mask per batch; this emits the CSR lists
+    blp_eval_rank consumes (unique, sorted column ids per query, global table rows).
+    """
+
+    def __init__(self, edges, ent2idx):
+        """edges: (E, 3) int64 array of (head, tail, rel) graph edges (duplicates allowed);
+        ent2idx: 1-D int64 array/tensor, entity id -> table row or -1."""
+        edges = np.asarray(edges, dtype=np.int64).reshape(-1, 3)
+        self.ent2idx = np.asarray(ent2idx.cpu() if torch.is_tensor(ent2idx) else ent2idx, dtype=np.int64)
+        self.n_ids = int(self.ent2idx.shape[0])
+        h, t, r = edges[:, 0], edges[:, 1], edges[:, 2]
+        self._tails = self._group(h, r, t)      # key (head, rel) -> tail ids
+        self._heads = self._group(t, r, h)      # key (tail, rel) -> head ids
+
+    def _key(self, ent, rel):
+        return rel * np.int64(self.n_ids + 1) + ent
+
+    def _group(self, ent, rel, other):
+        key = self._key(ent, rel)
+        order = np.lexsort((other, key))
+        key, other = key[order], other[order]
+        keep = np.ones(key.shape[0], bool)
+        keep[1:] = (key[1:] != key[:-1]) | (other[1:] != other[:-1])      # MultiDiGraph: parallel edges collapse
+        key, other = key[keep], other[keep]
+        ukey, start = np.unique(key, return_index=True)
+        return ukey, np.append(start, key.shape[0]).astype(np.int64), other
+
+    def _lookup(self, group, ent, rel, exclude):
+        ukey, start, other = group
+        key = self._key(ent, rel)
+        pos = np.searchsorted(ukey, key)
+        pos_c = np.minimum(pos, max(len(ukey) - 1, 0))
+        hit = (pos < len(ukey)) & (ukey[pos_c] == key) if len(ukey) else np.zeros(len(key), bool)
+        lists = []
+        for i in range(len(key)):
+            if not hit[i]:
+                lists.append(np.empty(0, np.int64))
+                continue
+            ids = other[start[pos[i]]:start[pos[i] + 1]]
+            ids = ids[ids != exclude[i]]                                   # utils.py:71,78: t != tail / h != head
+            cols = self.ent2idx[ids]
+            cols = np.unique(cols[cols != -1])                             # utils.py:72-74
+            lists.append(cols)
+        return lists
+
+    def csr(self, triples):
+        """triples: (B, 3) (head, tail, rel) entity IDS -> (indptr [2B+1], idx [nnz]) int64 numpy arrays,
+        head-prediction queries first, then tail-prediction queries (the reference's cat order)."""
+        triples = np.asarray(triples.cpu() if torch.is_tensor(triples) else triples, dtype=np.int64).reshape(-1, 3)
+        h, t, r = triples[:, 0], triples[:, 1], triples[:, 2]
+        heads_lists = self._lookup(self._heads, t, r, h)
+        tails_lists = self._lookup(self._tails, h, r, t)
+        lists = heads_lists + tails_lists
+        indptr = np.zeros(len(lists) + 1, np.int64)
+        np.cumsum([len(x) for x in lists], out=indptr[1:])
+        idx = np.concatenate(lists) if lists and indptr[-1] > 0 else np.empty(0, np.int64)
+        return indptr, idx
+
+    def dense_masks(self, triples, num_ents):
+        """The reference's return value (heads_filter, tails_filter) as dense bool arrays; test helper."""
+        indptr, idx = self.csr(triples)
+        b = (len(indptr) - 1) // 2
+        mask = np.zeros((2 * b, num_ents), bool)
+        for q in range(2 * b):
+            mask[q, idx[indptr[q]:indptr[q + 1]]] = True
+        return mask[:b], mask[b:]

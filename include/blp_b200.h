@@ -1,0 +1,176 @@
+/*
+ * blp_b200.h -- C ABI of the B200-native BLP scoring / loss / ranking path.
+ *
+ * The reference (dfdazac/blp) has no FFI: its seam is Python attribute binding
+ * (models.py:16-24 `self.score_fn = transe_score`, models.py:31-34
+ * `self.loss_fn = margin_loss`, utils.get_metrics called at train.py:153,167).
+ * This header is therefore the boundary a maintainer binds with ctypes (see
+ * INTEGRATION.md); each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a *borrowed device pointer* (cudaMalloc'd memory on the
+ *     current device) unless marked "host"; the library allocates nothing;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on
+ *     it, no call synchronises or copies to/from the host;
+ *   - return 0 on success, a negative BLP_E* code otherwise; the message is in
+ *     the thread-local blp_last_error();
+ *   - re-entrant: no global mutable state (DataParallel calls forward() from
+ *     one Python thread per device, train.py:330);
+ *   - fp32 only; rows are contiguous with `d` floats; D even for complex/simple
+ *     (torch.chunk(2, -1), models.py:231-233, 243-245).
+ */
+#ifndef BLP_B200_H
+#define BLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLP_B200_VERSION 100
+
+/* rel_model, models.py:16-26 */
+#define BLP_MODEL_TRANSE 0
+#define BLP_MODEL_DISTMULT 1
+#define BLP_MODEL_COMPLEX 2
+#define BLP_MODEL_SIMPLE 3
+/* loss_fn, models.py:31-36 */
+#define BLP_LOSS_MARGIN 0
+#define BLP_LOSS_NLL 1
+
+#define BLP_OK 0
+#define BLP_EINVAL (-1)   /* bad model / loss / shape / null pointer */
+#define BLP_EDIM (-2)     /* d not supported (odd d for complex/simple, d <= 0) */
+#define BLP_ECUDA (-3)    /* CUDA runtime error (message has the cudaError string) */
+#define BLP_EARCH (-4)    /* device is not sm_100 */
+
+int blp_version(void);
+const char *blp_last_error(void);
+/* 0 if `device` is a compute-capability 10.x GPU this library was built for. */
+int blp_device_check(int device);
+
+/* ---- a1-a4  score_fn(heads, tails, rels)  (models.py:222-248) ------------
+ * Materialising form, for direct callers of score_fn.  Operands are viewed as
+ * (A, C, d) with element strides (sA, sC) per operand, 0 = broadcast; covers
+ * the eval shapes (1,N,D)x(B,1,D)x(B,1,D) (train.py:146-147) and the train
+ * shapes (B,K,D)x(B,K,D)x(B,1,D) (models.py:57,67).  out is (A, C) row-major.
+ * Every score carries the same fp32 roundings as the reference's CPU path. */
+int blp_score_bcast(int model,
+                    const float *heads, int64_t hsA, int64_t hsC,
+                    const float *tails, int64_t tsA, int64_t tsC,
+                    const float *rels, int64_t rsA, int64_t rsC,
+                    int64_t A, int64_t C, int d, float *out, void *stream);
+
+/* ---- a11  utils.get_metrics  (utils.py:86-111) ----------------------------
+ * Integer part on a materialised (q, n) score matrix with row stride
+ * `row_stride` floats: gt[i] = #{j: s_ij > s_i,true}, ge[i] = #{j: s_ij >= ..}
+ * (best_rank = gt + 1, worst_rank = ge). */
+int blp_rank_counts(const float *pred, int64_t q, int64_t n, int64_t row_stride,
+                    const int64_t *true_idx, int32_t *gt, int32_t *ge, void *stream);
+/* Float part: avg = float(gt + 1 + ge) * 0.5; recip = 1/avg; hits = avg <= k.
+ * k_values is a HOST array of nk ints (nk <= 8); hits is (q, nk) bytes. */
+int blp_metrics_from_counts(const int32_t *gt, const int32_t *ge, int64_t q,
+                            const int64_t *k_values_host, int nk,
+                            float *recip, uint8_t *hits, void *stream);
+
+/* train.py:154-157: sums[0] = sum_i 1/avg_i, sums[1 + j] = #{i: avg_i <= k_j}
+ * over q queries, accumulated in fp64 in a fixed order.  sums is a DEVICE array
+ * of 1 + nk doubles (overwritten); k_values is a HOST array. */
+int blp_metrics_reduce(const int32_t *gt, const int32_t *ge, int64_t q,
+                       const int64_t *k_values_host, int nk, double *sums, void *stream);
+
+/* ---- a10 + a11 + a12  fused full-entity scoring and ranking ---------------
+ * Replaces train.py:141-171 for one batch (or a whole sweep: b is unbounded):
+ * queries 0..b-1 predict the head (every candidate row plays `heads`,
+ * train.py:146), queries b..2b-1 predict the tail (train.py:147); no
+ * (2b, n) score matrix is written.
+ *   ent        [n_local, d]  this rank's shard of the entity table
+ *   ent_offset global row id of ent[0] (filter indices are global)
+ *   h_rows, t_rows, r_rows [b, d]  gathered true head / true tail / relation
+ *              rows (train.py:141-143); the true entity's score is computed
+ *              from these rows, so every shard derives identical bits
+ *   filt_indptr [2b+1], filt_idx [nnz]  CSR of filtered candidate rows per
+ *              query (global ids, unique per query; the true entity is never
+ *              listed, utils.py:71,78), or NULL for raw ranks only
+ *   gt, ge     [2b] raw counts over this shard (overwritten)
+ *   gt_f, ge_f [2b] filtered counts (overwritten; may be NULL iff filt is NULL)
+ *   true_score [2b] score of the true triple (overwritten)
+ * Counts are integers, so sums over shards are exact for any partition. */
+int blp_eval_rank(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                  const float *h_rows, const float *t_rows, const float *r_rows, int64_t b,
+                  const int64_t *filt_indptr, const int64_t *filt_idx,
+                  int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f,
+                  float *true_score, void *stream);
+
+/* ---- a5-a8  LinkPrediction.compute_loss, forward + backward ---------------
+ * Replaces models.py:51-70 and its autograd graph with one fused pass.
+ *   ent_embs   [b, 2, d]     (models.py:56 chunk -> heads, tails)
+ *   rel_weight [num_rel, d], rels [b] int64   (models.py:55 rel_emb lookup)
+ *   neg_idx    int64, logical (b, k, 2) with element strides (s0, s1, s2): the
+ *              reference sampler returns a transposed view (data.py:78-79);
+ *              values index ent_embs.view(2b, d) (models.py:65)
+ *   regularizer  models.py:59-62 (0 = off)
+ *   loss_out   [1]   model_loss + reg_loss (models.py:70)
+ *   pos_scores [b], neg_scores [b, k]   (written; neg_scores may be NULL)
+ *   grad_ent [b,2,d], grad_rel_weight [num_rel,d]: d loss / d ent_embs and
+ *              d loss / d rel_emb.weight (dense, like nn.Embedding's backward)
+ *              for an upstream gradient of 1, or both NULL for forward only.
+ *              Both are overwritten.  (The loss is linear in the upstream
+ *              gradient, so autograd's backward is blp_scale by grad_out.)
+ *   workspace  blp_train_workspace_bytes(b, k) bytes, zero-filled once by the
+ *              caller; the call leaves it zero-filled again.  One workspace
+ *              per concurrently running stream.
+ * Conventions follow the reference ops: margin mask keeps gradient where
+ * 1 - pos + neg == 0 (models.py:253), sign(0) = 0 for TransE, softplus
+ * threshold 20 (models.py:258). */
+int64_t blp_train_workspace_bytes(int64_t b, int64_t k);
+int blp_train_loss(int model, int loss, const float *ent_embs, const float *rel_weight,
+                   const int64_t *rels, int64_t num_rel,
+                   const int64_t *neg_idx, int64_t s0, int64_t s1, int64_t s2,
+                   int64_t b, int64_t k, int d, float regularizer,
+                   float *loss_out, float *pos_scores, float *neg_scores,
+                   float *grad_ent, float *grad_rel_weight, void *workspace, void *stream);
+
+/* y[i] = x[i] * *scale_dev (scale_dev is a DEVICE scalar; y may alias x):
+ * autograd's backward of the fused loss multiplies the stored unit-upstream
+ * gradients by grad_output. */
+int blp_scale(float *y, const float *x, const float *scale_dev, int64_t n, void *stream);
+
+/* ---- a5, a6  loss_fn(pos_scores, neg_scores)  (models.py:251-258) ----------
+ * Stand-alone form for direct callers of margin_loss / nll_loss on
+ * materialised scores: pos [b], neg (b, k) with row stride neg_row_stride.
+ * loss_out [1]; grad_pos [b] and grad_neg [b, k] (contiguous) receive
+ * d loss / d pos and d loss / d neg, either may be NULL. */
+int blp_pair_loss(int loss, const float *pos, const float *neg, int64_t neg_row_stride,
+                  int64_t b, int64_t k, float *loss_out, float *grad_pos, float *grad_neg,
+                  void *stream);
+/* ---- a7  l2_regularization(heads, tails, rels)  (models.py:261-266) --------
+ * out[0] = (mean(heads^2) + mean(tails^2) + mean(rels^2)) / 3 over contiguous
+ * tensors of n_* elements. */
+int blp_l2_regularization(const float *heads, int64_t n_heads, const float *tails, int64_t n_tails,
+                          const float *rels, int64_t n_rels, float *out, void *stream);
+
+/* ---- measurement aid ------------------------------------------------------
+ * FP32 pipe micro-benchmarks used by bench.py to measure the lane-op rate the
+ * ALU-bound exact sweeps are compared against ("measure
+ * with a microbenchmark").  Every thread of a full grid runs `iters` rounds of
+ * 16 independent dependency chains of the chosen instruction mix and writes one
+ * float to sink[n_threads]:
+ *   0 = FADD            acc = acc + c
+ *   1 = FADD |x|        acc = acc + |u - e|   (2 FADD, the TransE tail-pred step)
+ *   2 = add.f32x2       two chains per instruction
+ *   3 = f32x2 TransE    {acc0,acc1} += |{u0,u1} - {e,e}|  (2 packed adds + 2 LOP)
+ *   4 = FMUL + FADD     acc = acc + v * e     (the DistMult tail-pred step, unfused)
+ * *lane_ops_host receives the number of fp32 lane operations issued (adds and
+ * multiplies; the integer AND of variant 3 is not counted). */
+int blp_pipe_probe(int variant, float *sink, int64_t n_threads, int iters, double *lane_ops_host, void *stream);
+
+/* Number of kernels the last call on this thread launched (bench.py's
+ * `gpu_launches` is counted from this). */
+int blp_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLP_B200_H */

@@ -291,8 +291,11 @@ int blp_oracle_eval_rank(int model, const float *ent, int64_t n, int d,
             const int head_pred = q < b;
             const int64_t i = head_pred ? q : q - b;
             const float *hq = h_rows + i * d, *tq = t_rows + i * d, *rq = r_rows + i * d;
-            const int64_t tix = head_pred ? head_idx[i] : tail_idx[i];
-            const float *e_true = ent + tix * d;
+            /* pred.gather(true_idx) (utils.py:103).  With head_idx / tail_idx == NULL the true row is taken
+             * from the gathered query rows themselves (h_rows[i] IS ent[head_idx[i]], train.py:141-142), which
+             * is what a candidate-sharded caller must do when the true row lives in another shard. */
+            const float *e_true = head_pred ? (head_idx ? ent + head_idx[i] * d : hq)
+                                            : (tail_idx ? ent + tail_idx[i] * d : tq);
             const float st = head_pred ? score_one(model, e_true, tq, rq, d, buf)
                                        : score_one(model, hq, e_true, rq, d, buf);
             int64_t a = 0, c = 0;

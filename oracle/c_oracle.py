@@ -119,8 +119,8 @@ def eval_rank(model, ent, h_rows, t_rows, r_rows, head_idx, tail_idx,
     h, hp = _f(h_rows)
     t, tp = _f(t_rows)
     r, rp = _f(r_rows)
-    hi, hip = _i(head_idx)
-    ti, tip = _i(tail_idx)
+    hi, hip = _i(head_idx) if head_idx is not None else (None, None)
+    ti, tip = _i(tail_idx) if tail_idx is not None else (None, None)
     n, d = ent.shape
     b = h.shape[0]
     gt = np.empty(2 * b, np.int64); ge = np.empty(2 * b, np.int64)

@@ -1,0 +1,176 @@
+"""Host-side logic on CPU: filter CSR construction (utils.py:46-83), row sharding, the
+sweep's chunking / collective plumbing (world_size 2 over gloo), and the end-to-end
+eval metrics against the reference's eval_link_prediction run (golden eval_loop_*).
+The per-shard counting is done by the ORACLE here (count_fn seam) -- the CUDA kernels
+are covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import c_oracle
+
+import blp_b200
+from blp_b200.evaluate import _slice_csr, rank_sweep, shard_bounds
+from blp_b200.utils import TripleFilterIndex, make_ent2idx
+
+MODELS = ("transe", "distmult", "complex", "simple")
+
+
+def oracle_count_fn(model, ent, h_rows, t_rows, r_rows, indptr, idx, ent_offset):
+    """Stand-in for ops.eval_rank on CPU tensors: counts over THIS shard, filter ids are global."""
+    n_local = ent.shape[0]
+    b = h_rows.shape[0]
+    fi = fp = None
+    if indptr is not None:
+        indptr, idx = indptr.numpy(), idx.numpy()
+        lists = []
+        for q in range(2 * b):
+            cols = idx[indptr[q]:indptr[q + 1]] - ent_offset
+            lists.append(cols[(cols >= 0) & (cols < n_local)])
+        fp = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+        fi = np.concatenate(lists) if fp[-1] else np.zeros(0, np.int64)
+    if n_local == 0:
+        z = np.zeros(2 * b, np.int64)
+        out = dict(gt=z, ge=z, gt_f=z, ge_f=z, true_score=np.zeros(2 * b, np.float32))
+    else:
+        out = c_oracle.eval_rank(model, ent.numpy(), h_rows.numpy(), t_rows.numpy(), r_rows.numpy(), None, None, fp, fi)
+    res = {k: torch.from_numpy(np.asarray(v)).to(torch.int32) for k, v in out.items() if k != "true_score"}
+    res["true_score"] = torch.from_numpy(out["true_score"])
+    return res
+
+
+def reference_filters(triples, edges, num_ents, ent2idx):
+    """utils.get_triple_filters restated literally over an edge list (utils.py:46-83)."""
+    hf = np.zeros((len(triples), num_ents), bool)
+    tf = np.zeros_like(hf)
+    for i, (head, tail, rel) in enumerate(triples.tolist()):
+        for h, t, r in edges.tolist():
+            if h == head and r == rel and t != tail and ent2idx[t] != -1:
+                tf[i, ent2idx[t]] = True
+            if t == tail and r == rel and h != head and ent2idx[h] != -1:
+                hf[i, ent2idx[h]] = True
+    return hf, tf
+
+
+def test_make_ent2idx_docstring_case():
+    assert make_ent2idx(torch.tensor([4, 5, 0]), 5).tolist() == [2, -1, -1, -1, 0, 1]     # utils.py:36-38
+
+
+def test_shard_bounds_cover_and_disjoint():
+    for n in (0, 1, 7, 135, 14541, 4800000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_filter_index_matches_reference_semantics():
+    g = golden("eval_loop_transe")
+    ent2idx = make_ent2idx(torch.from_numpy(g["entities"]), int(g["n_ids"]) - 1).numpy()
+    fidx = TripleFilterIndex(g["graph_edges"], ent2idx)
+    n = len(g["entities"])
+    hf, tf = fidx.dense_masks(g["triples"], n)
+    rhf, rtf = reference_filters(g["triples"], g["graph_edges"], n, ent2idx)
+    assert np.array_equal(hf, rhf) and np.array_equal(tf, rtf)
+    assert rhf.sum() + rtf.sum() > 0
+    # chunk slicing of a whole-sweep CSR
+    indptr, idx = fidx.csr(g["triples"])
+    T = len(g["triples"])
+    sub_ptr, sub_idx = _slice_csr((indptr, idx), 16, 48, T)
+    ref_ptr, ref_idx = fidx.csr(g["triples"][16:48])
+    assert np.array_equal(sub_ptr, ref_ptr) and np.array_equal(sub_idx, ref_idx)
+
+
+def _loop_inputs(model):
+    g = golden("eval_loop_" + model)
+    ent2idx = make_ent2idx(torch.from_numpy(g["entities"]), int(g["n_ids"]) - 1)
+    triples = torch.from_numpy(g["triples"])
+    rows = torch.stack([ent2idx[triples[:, 0]], ent2idx[triples[:, 1]], triples[:, 2]], dim=1)
+    fidx = TripleFilterIndex(g["graph_edges"], ent2idx)
+    return g, rows, fidx
+
+
+def _metrics(out, T):
+    res = {}
+    for suffix, tag in (("", ""), ("_f", "_filt")):
+        gt, ge = out["gt" + suffix].reshape(-1).numpy(), out["ge" + suffix].reshape(-1).numpy()
+        recip, hits = c_oracle.metrics_from_counts(gt, ge, [1, 3, 10])
+        res["test_mrr" + tag] = float(recip.astype(np.float64).sum() / (2 * T))
+        for j, k in enumerate((1, 3, 10)):
+            res[f"test_hits@{k}{tag}"] = float(hits[:, j].sum() / (2 * T))
+        res["recip" + suffix] = recip.reshape(2, T)
+    return res
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("chunk", (16, 40, 1000))
+def test_sweep_reproduces_reference_eval_loop(model, chunk):
+    g, rows, fidx = _loop_inputs(model)
+    T = rows.shape[0]
+    out = rank_sweep(model, torch.from_numpy(g["ent_emb"]), torch.from_numpy(g["rel_weight"]), rows,
+                     filter_index=fidx, filter_triples=g["triples"], chunk=chunk, count_fn=oracle_count_fn)
+    m = _metrics(out, T)
+    want = dict(zip(g["scalar_names"].tolist(), g["scalar_values"].tolist()))
+    for name in ("test_mrr", "test_mrr_filt", "test_hits@1", "test_hits@3", "test_hits@10",
+                 "test_hits@1_filt", "test_hits@3_filt", "test_hits@10_filt"):
+        assert abs(m[name] - want[name]) <= 1e-6, (name, m[name], want[name])
+    # by-position breakdown (utils.py:114-148) from the per-query reciprocals
+    new = set(g["new_entities"].tolist())
+    rf = m["recip_f"]
+    sums, cnts = np.zeros(3), np.zeros(3)
+    for i, (h, t, _) in enumerate(g["triples"].tolist()):
+        v = (float(rf[0, i]) + float(rf[1, i])) / 2.0
+        slot = 0 if (h in new and t in new) else 1 if h in new else 2 if t in new else None
+        if slot is not None:
+            sums[slot] += v
+            cnts[slot] += 1
+    cnts[cnts < 1] = 1
+    for slot, name in enumerate(("test_mrr_filt_both_new", "test_mrr_filt_head_new", "test_mrr_filt_tail_new")):
+        assert abs(sums[slot] / cnts[slot] - want[name]) <= 1e-5, name
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, model, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, rows, fidx = _loop_inputs(model)
+        table = torch.from_numpy(g["ent_emb"])
+        lo, hi = shard_bounds(table.shape[0], world, rank)
+        out = rank_sweep(model, table[lo:hi].contiguous(), torch.from_numpy(g["rel_weight"]), rows,
+                         filter_index=fidx, filter_triples=g["triples"], chunk=40, ent_offset=lo,
+                         count_fn=oracle_count_fn)
+        if rank == 0:
+            ret.update({k: out[k].numpy() for k in ("gt", "ge", "gt_f", "ge_f")})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", ("transe", "complex"))
+@pytest.mark.parametrize("world", (2, 3))
+def test_sharded_sweep_equals_single_rank_gloo(model, world):
+    import torch.multiprocessing as mp
+    g, rows, fidx = _loop_inputs(model)
+    single = rank_sweep(model, torch.from_numpy(g["ent_emb"]), torch.from_numpy(g["rel_weight"]), rows,
+                        filter_index=fidx, filter_triples=g["triples"], count_fn=oracle_count_fn)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), model, ret), nprocs=world, join=True)
+    for k in ("gt", "ge", "gt_f", "ge_f"):
+        assert np.array_equal(ret[k], single[k].numpy()), k      # integer sums: bit-identical for any world size
+
+
+def test_gather_rows_single_process_matches_index():
+    table = torch.randn(50, 8)
+    idx = torch.tensor([3, 49, 0, 3])
+    assert torch.equal(blp_b200.gather_rows(table, 0, idx), table[idx])

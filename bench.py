@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- triples scored / second on the BLP scoring-and-ranking hot path (BASELINE.json).
+
+One STEP = one pass of the hot path over one batch of synthetic FB15k-237-shaped input:
+  * one training step of LinkPrediction.compute_loss forward + backward (models.py:51-70)
+    on B positives with K in-batch negatives each              -> B * (K + 1) triples scored
+  * one evaluation chunk of E test triples ranked against ALL N entities, heads and tails
+    (train.py:128-157)                                         -> 2 * E * N triples scored
+`value` = triples scored per second with inputs resident in HBM (CUDA-event timed, max over ranks);
+`e2e`   = the same metric through the public API with HOST (pinned) inputs, H2D/D2H inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): every rank runs the same per-GPU work on its own batch
+(train replicas are independent exactly like the reference's DataParallel sub-batches; eval
+queries are sharded, table replicated: SURVEY.md section 8e "small tables") -> weak scaling, no data-path
+collective.  The entity-sharded sweep with its one all-reduce is exercised by `--sharded-sweep`.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (N entities, R relations, T test triples)
+    "fb15k237": (14541, 237, 20480),
+    "wn18rr": (40943, 11, 3136),
+    "umls": (135, 46, 661),
+}
+METRIC = "triples scored/sec (train negs + eval full-entity rank)"
+UNIT = "triples/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    p.add_argument("--dataset", default="fb15k237", choices=sorted(CONFIGS))
+    p.add_argument("--model", default="transe", choices=("transe", "distmult", "complex", "simple"))
+    p.add_argument("--loss", default="margin", choices=("margin", "nll"))
+    p.add_argument("--dim", type=int, default=128)
+    p.add_argument("--train-batch", type=int, default=64)
+    p.add_argument("--negatives", type=int, default=512)
+    p.add_argument("--eval-batch", type=int, default=1024, help="test triples ranked per step (E)")
+    p.add_argument("--ref-eval-batch", type=int, default=128, help="E of the bounded CPU sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------ workload ----
+def make_workload(args):
+    """Synthetic FB15k-237-shaped inputs, fixed seeds; CPU tensors."""
+    n, r, t = CONFIGS[args.dataset]
+    d, b, k = args.dim, args.train_batch, args.negatives
+    g = torch.Generator().manual_seed(0)
+    ent = torch.randn(n, d, generator=g)
+    if args.model == "transe":
+        ent = torch.nn.functional.normalize(ent, dim=-1)                  # models.py:40-41
+    g = torch.Generator().manual_seed(1)
+    a = (6.0 / (r + d)) ** 0.5
+    rel = (torch.rand(r, d, generator=g) * 2 - 1) * a                      # xavier_uniform_, models.py:29
+    g = torch.Generator().manual_seed(2)
+    triples = torch.stack([torch.randint(0, n, (t,), generator=g), torch.randint(0, n, (t,), generator=g),
+                           torch.randint(0, r, (t,), generator=g)], dim=1)
+    g = torch.Generator().manual_seed(3)
+    pairs = torch.randint(0, n, (b, 2), generator=g)
+    rels = torch.randint(0, r, (b, 1), generator=g)
+    # in-batch negatives with the structure and the memory layout of data.py:35-81: storage (K, B, 2),
+    # returned transposed to (B, K, 2); one column keeps the row's own entity, the other is a random
+    # in-batch entity of another row
+    own = torch.arange(2 * b).reshape(b, 2)
+    neg = own.repeat(k, 1).reshape(k, b, 2).clone()
+    w = torch.ones(b, 2 * b)
+    w.scatter_(1, own, torch.zeros(b, 2))
+    repl = w.multinomial(k, replacement=True, generator=g).t()             # (K, B)
+    col = torch.randint(0, 2, (k, b), generator=g)
+    neg[torch.arange(k)[:, None], torch.arange(b)[None, :], col] = repl
+    return {"ent": ent, "rel": rel, "triples": triples, "pairs": pairs, "rels": rels, "neg_storage": neg,
+            "n": n, "r": r, "t": t, "d": d, "b": b, "k": k}
+
+
+def step_triples(w, e):
+    return w["b"] * (w["k"] + 1) + 2 * e * w["n"]
+
+
+# ----------------------------------------------------------------- clocks ----
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        rows = [ln for (ts, ln) in self.lines if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.06)]
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------- CPU reference arm ----
+def cpu_reference_step(w, args, e, lo):
+    """The reference's CPU execution strategy (stock ATen ops, materialised broadcasts) on one bounded
+    sample: one compute_loss forward+backward and E test triples in eval batches of 64 (train.py:128-157)."""
+    from oracle import torch_port
+    ent_embs = w["ent"][w["pairs"]].clone().requires_grad_(True)           # (B,2,D)
+    rel_w = w["rel"].clone().requires_grad_(True)
+    neg_idx = w["neg_storage"].transpose(0, 1)                             # (B,K,2) non-contiguous view
+    loss = torch_port.batch_loss(args.model, args.loss, ent_embs, rel_w[w["rels"][:, 0]], neg_idx, 0.0)
+    loss.backward()
+    ent_emb = w["ent"].unsqueeze(0)
+    k_values = torch.tensor([[1, 3, 10]])
+    mrr = 0.0
+    for s in range(lo, lo + e, 64):
+        tr = w["triples"][torch.arange(s, min(s + 64, lo + e)) % w["t"]]
+        out = torch_port.eval_batch(args.model, ent_emb, tr[:, 0:1], tr[:, 1:2], w["rel"][tr[:, 2:3]], k_values)
+        mrr += out["recip"].sum().item()
+    return float(loss.item()), mrr
+
+
+def run_cpu_reference(w, args, steps, warmup):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    e = args.ref_eval_batch
+    for i in range(warmup):
+        cpu_reference_step(w, args, e, (i * e) % w["t"])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_reference_step(w, args, e, ((warmup + i) * e) % w["t"])
+    dt = time.perf_counter() - t0
+    return {"value": steps * step_triples(w, e) / dt, "seconds": dt, "cores": torch.get_num_threads(),
+            "ms_per_step": 1e3 * dt / steps,
+            "sample": f"{steps} step(s) of: 1 compute_loss fwd+bwd (B={w['b']}, K={w['k']}) + {e} test triples ranked "
+                      f"against all {w['n']} entities in eval batches of 64 (reference eval_batch_size), "
+                      f"ATen-op restatement of the reference's CPU path (oracle/torch_port.py), {threads} torch threads"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = make_workload(args)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # bound the whole run to a few minutes: one sample step costs ~2 s on 8 cores
+    t0 = time.perf_counter()
+    cpu_reference_step(w, args, args.ref_eval_batch, 0)
+    one = time.perf_counter() - t0
+    budget = 150.0
+    if (steps + warmup) * one > budget:
+        warmup = min(warmup, 1)
+        steps = max(1, int(budget / one) - warmup)
+    res = run_cpu_reference(w, args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, w, args.ref_eval_batch, flush=False),
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, w, e, flush):
+    return {"workload": f"synthetic {args.dataset} ({w['n']} entities, {w['r']} relations) BLP-{args.model} dim={w['d']}: "
+                        f"1 compute_loss fwd+bwd (B={w['b']}, K={w['k']} negatives, {args.loss} loss) + {e} test triples "
+                        f"ranked against all entities (heads and tails) per step",
+            "entities": w["n"], "relations": w["r"], "dim": w["d"], "rel_model": args.model, "loss": args.loss,
+            "train_batch": w["b"], "negatives": w["k"], "eval_triples_per_step": e,
+            "triples_per_step": step_triples(w, e),
+            "l2": ("flushed between timed steps (256 MiB write)" if flush else "not flushed (table is L2-resident by design)"),
+            "parallelism": f"replicas x{args.gpus}: train sub-batches independent, eval queries sharded, table replicated"}
+
+
+# ----------------------------------------------------------------- B200 arm ----
+def main_b200(args):
+    import torch.distributed as dist
+
+    import blp_b200
+    from blp_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    w = make_workload(args)
+    e, b, k, d, n, t = args.eval_batch, w["b"], w["k"], w["d"], w["n"], w["t"]
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    flush = not args.no_flush
+
+    # ---- resident inputs (value): everything already in HBM
+    ent = w["ent"].to(dev)
+    model = blp_b200.TransductiveLinkPrediction(d, args.model, args.loss, 8, w["r"], 0).to(dev)
+    with torch.no_grad():
+        model.rel_emb.weight.copy_(w["rel"])
+    rel_w = model.rel_emb.weight
+    # each rank works on its own slice of the test triples / its own training sub-batch
+    triples = w["triples"].roll(-rank * e, 0).to(dev)
+    ent_embs = ent[w["pairs"].to(dev)].contiguous()
+    rels = w["rels"].to(dev)
+    neg = w["neg_storage"].to(dev).transpose(0, 1)                         # (B,K,2), strides of the reference sampler
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+    # pre-gathered query rows per eval chunk (train.py:141-143 gathers are part of the step: done inside)
+
+    launches = {"n": 0}
+
+    def train_step():
+        x = ent_embs.detach().requires_grad_(True)
+        rel_w.grad = None
+        loss = model.compute_loss(x, rels, neg)
+        loss.backward()
+        launches["n"] += 1 + 2            # fused fwd+bwd kernel, 2 x blp_scale in autograd's backward
+        return loss
+
+    def eval_step(i):
+        lo = (i * e) % t
+        idx = torch.arange(lo, lo + e, device=dev) % t
+        out = blp_b200.rank_sweep(args.model, ent, rel_w, triples.index_select(0, idx), chunk=e)
+        launches["n"] += out["launches"]
+        return out
+
+    def step(i):
+        loss = train_step()
+        out = eval_step(i)
+        return loss, out
+
+    # profile events for the dominant kernel (the eval sweep kernel)
+    prof = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a_, b_ in prof + step_ev:          # materialise the cudaEvent_t handles
+        a_.record(); b_.record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    launches["n"] = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.12)
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        if flush:
+            flush_buf.fill_(i & 0xFF)
+        step_ev[i][0].record()
+        lib.blp_profile_events(1, ctypes.c_void_p(prof[i][0].cuda_event), ctypes.c_void_p(prof[i][1].cuda_event))
+        step(warmup + i)
+        step_ev[i][1].record()
+    lib.blp_profile_events(0, None, None)
+    barrier()
+    t_wall1 = time.perf_counter()
+    timed_launches = launches["n"]
+    step_ms = [a_.elapsed_time(b_) for a_, b_ in step_ev]
+    kern_ms = [a_.elapsed_time(b_) for a_, b_ in prof]
+    total_ms = sum(step_ms)
+    # keep the GPU under the same load until nvidia-smi has a few samples, if the timed region was short
+    if t_wall1 - t_wall0 < 1.0:
+        t_end = time.perf_counter() + 1.0
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i); i += 1
+            if i % 16 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = world * steps * step_triples(w, e) / (total_ms * 1e-3)
+
+    # ---- e2e: public API, host (pinned) inputs, H2D + D2H inside the timed region
+    pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
+    h_ent_embs = pin(w["ent"][w["pairs"]])
+    h_rels = pin(w["rels"])
+    h_neg = pin(w["neg_storage"])
+    h_triples = [pin(w["triples"][(torch.arange(i * e, (i + 1) * e) + rank * e) % t]) for i in range(max(1, t // e))]
+    h2d = h_ent_embs.numel() * 4 + h_rels.numel() * 8 + h_neg.numel() * 8 + h_triples[0].numel() * 8
+    d2h = 4 + 4 * 8
+
+    def e2e_step(i):
+        x = h_ent_embs.to(dev, non_blocking=True).requires_grad_(True)
+        r_ = h_rels.to(dev, non_blocking=True)
+        ng = h_neg.to(dev, non_blocking=True).transpose(0, 1)
+        tr = h_triples[i % len(h_triples)].to(dev, non_blocking=True)
+        rel_w.grad = None
+        loss = model.compute_loss(x, r_, ng)
+        loss.backward()
+        out = blp_b200.rank_sweep(args.model, ent, rel_w, tr, chunk=e)
+        return loss.item(), blp_b200.finalize(out)                           # D2H: loss scalar + 4 fp64 accumulators
+
+    for i in range(warmup):
+        e2e_step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = steps
+    ev0.record()
+    for i in range(e2e_steps):
+        last = e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = world * e2e_steps * step_triples(w, e) / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (eval sweep kernel), measured live above
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    kern_s = statistics.mean(kern_ms) * 1e-3
+    alg_bytes = n * d * 4 + e * 3 * d * 4 + 2 * e * 4 + 2 * e * 2 * 4      # table once + query rows + s_true + counters
+    lane_ops_per = {"transe": 2.5, "distmult": 2.5, "complex": 5.0, "simple": 2.5}[args.model] * d  # head/tail mean
+    probe = measure_fp32_rate(ops, dev, args.model)
+    roofline = {
+        "bound": "hbm", "kernel": f"sweep_kernel<{args.model}>", "achieved": alg_bytes / kern_s / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
+        "kernel_share_of_step": statistics.mean(kern_ms) / statistics.mean(step_ms),
+        "binding": "fp32 ALU (exact-order arithmetic): with Q >= ~11 queries per table pass the sweep is bound by "
+                   "FP32 lane-ops, not HBM (DESIGN.md); the HBM fraction is reported because the contract asks for it",
+        "alu": {"lane_ops_per_launch": 2 * e * n * lane_ops_per, "achieved_tlaneops": 2 * e * n * lane_ops_per / kern_s / 1e12,
+                "peak_tlaneops": probe, "frac": (2 * e * n * lane_ops_per / kern_s / 1e12) / probe if probe else None,
+                "peak_source": "blp_pipe_probe (same instruction mix, measured in this run)"},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = run_cpu_reference(w, args, steps=max(1, int(12.0 / max(0.5, 2.0))), warmup=1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args, w, e, flush),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / e2e_steps, "last_loss": last[0], "last_mrr": last[1]["mrr"]},
+        "gpu_launches": timed_launches,
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_fp32_rate(ops, dev, model):
+    """FP32 lane-op rate of the instruction mix the sweep issues (T lane-ops/s), best of 3."""
+    variant = 1 if model == "transe" else 4
+    best = 0.0
+    try:
+        for _ in range(4):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            lane_ops, _ = ops.pipe_probe(variant, dev, n_threads=148 * 8 * 256, iters=8192)
+            b_.record()
+            torch.cuda.synchronize()
+            best = max(best, lane_ops / (a_.elapsed_time(b_) * 1e-3) / 1e12)
+    except Exception:   # measurement aid only
+        return None
+    return best
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

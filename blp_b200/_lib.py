@@ -32,6 +32,7 @@ SYMBOLS = {
     "blp_scale": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "blp_pair_loss": (_i32, [_i32, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "blp_l2_regularization": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "blp_profile_events": (_i32, [_i32, _vp, _vp]),
     "blp_pipe_probe": (_i32, [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

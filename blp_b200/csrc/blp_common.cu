@@ -17,6 +17,16 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static thread_local int tl_prof_which = 0;
+static thread_local cudaEvent_t tl_prof_start = nullptr, tl_prof_stop = nullptr;
+
+void prof_begin(int which, cudaStream_t st) {
+    if (which == tl_prof_which && tl_prof_start) cudaEventRecord(tl_prof_start, st);
+}
+void prof_end(int which, cudaStream_t st) {
+    if (which == tl_prof_which && tl_prof_stop) cudaEventRecord(tl_prof_stop, st);
+}
+
 void count_launch(int n) { tl_launches += n; }
 void reset_launch_count() { tl_launches = 0; }
 
@@ -33,6 +43,14 @@ extern "C" int blp_version(void) { return BLP_B200_VERSION; }
 extern "C" const char *blp_last_error(void) { return blp::tl_error; }
 
 extern "C" int blp_last_launch_count(void) { return blp::tl_launches; }
+
+extern "C" int blp_profile_events(int which, void *start_event, void *stop_event) {
+    if (which < 0 || which > 2) { blp::set_error("which must be 0 (off), 1 (eval sweep kernel) or 2 (train kernel)"); return BLP_EINVAL; }
+    blp::tl_prof_which = which;
+    blp::tl_prof_start = which ? (cudaEvent_t)start_event : nullptr;
+    blp::tl_prof_stop = which ? (cudaEvent_t)stop_event : nullptr;
+    return BLP_OK;
+}
 
 extern "C" int blp_device_check(int device) {
     cudaDeviceProp p;

@@ -19,6 +19,9 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 void reset_launch_count();
 int check_cuda(cudaError_t e, const char *what);
+// measurement aid (blp_profile_events): bracket the selected kernel with the caller's CUDA events
+void prof_begin(int which, cudaStream_t st);
+void prof_end(int which, cudaStream_t st);
 
 #define BLP_CUDA(call)                                 \
     do {                                               \

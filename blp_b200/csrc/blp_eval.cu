@@ -620,7 +620,9 @@ static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
     if (groups > 65535) { set_error("too many query groups (%lld); split the sweep", groups); return BLP_EINVAL; }
     const int splits = pick_splits(ntiles, groups, num_sms());
     dim3 grid((unsigned)splits, (unsigned)groups);
+    prof_begin(1, st);
     sweep_kernel<MODEL><<<grid, kThreads, smem, st>>>(a);
+    prof_end(1, st);
     count_launch();
     BLP_CUDA(cudaGetLastError());
     return BLP_OK;

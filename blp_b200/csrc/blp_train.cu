@@ -363,8 +363,10 @@ __global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a)
 template <int MODEL, int NCH2, int ILP>
 static int launch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
     const unsigned grid = (unsigned)(a.b * a.slices);
+    prof_begin(2, st);
     if (grad) train_kernel<MODEL, NCH2, ILP, true><<<grid, kTrainThreads, 0, st>>>(a);
     else train_kernel<MODEL, NCH2, ILP, false><<<grid, kTrainThreads, 0, st>>>(a);
+    prof_end(2, st);
     count_launch();
     return check_cuda(cudaGetLastError(), "train_kernel launch");
 }

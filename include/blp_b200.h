@@ -166,6 +166,13 @@ int blp_l2_regularization(const float *heads, int64_t n_heads, const float *tail
  * multiplies; the integer AND of variant 3 is not counted). */
 int blp_pipe_probe(int variant, float *sink, int64_t n_threads, int iters, double *lane_ops_host, void *stream);
 
+/* Bracket the dominant kernel of the following calls on THIS thread with the
+ * caller's CUDA events (cudaEvent_t passed as void*), recorded on the stream the
+ * kernel is launched on: which = 1 the eval sweep kernel (blp_eval_rank /
+ * blp_score_bcast fast path), 2 the fused train kernel, 0 switches it off.
+ * bench.py uses this for the per-launch duration behind `roofline.achieved`. */
+int blp_profile_events(int which, void *start_event, void *stop_event);
+
 /* Number of kernels the last call on this thread launched (bench.py's
  * `gpu_launches` is counted from this). */
 int blp_last_launch_count(void);

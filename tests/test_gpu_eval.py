@@ -1,0 +1,204 @@
+"""CUDA eval path vs the oracle and the golden vectors (through the C ABI).
+Bit-exact: every score, every integer rank counter, reciprocal ranks and hits."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names, mask_to_csr, unpack_mask
+from oracle import c_oracle
+
+import blp_b200
+from blp_b200 import ops
+
+pytestmark = pytest.mark.gpu
+EVAL = [n for n in golden_names("eval_") if not n.startswith("eval_loop")]
+MODELS = ("transe", "distmult", "complex", "simple")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def make_inputs(model, n, d, b, seed, n_rel=11):
+    g = torch.Generator().manual_seed(seed)
+    ent = torch.randn(n, d, generator=g)
+    if model == "transe":
+        ent = torch.nn.functional.normalize(ent, dim=-1)
+    a = (6.0 / (n_rel + d)) ** 0.5
+    rel = (torch.rand(n_rel, d, generator=g) * 2 - 1) * a
+    heads = torch.randint(0, n, (b,), generator=g)
+    tails = torch.randint(0, n, (b,), generator=g)
+    rels = torch.randint(0, n_rel, (b,), generator=g)
+    return ent, rel, heads, tails, rels
+
+
+@pytest.mark.parametrize("name", EVAL)
+def test_golden_eval_rank(name, cuda_device):
+    g = golden(name)
+    model = name.split("_")[1]
+    heads, tails, rels = g["heads"][:, 0], g["tails"][:, 0], g["rels"][:, 0]
+    indptr, idx = mask_to_csr(unpack_mask(g))
+    ent = _t(g["ent"], cuda_device)
+    out = ops.eval_rank(model, ent, _t(g["ent"][heads], cuda_device), _t(g["ent"][tails], cuda_device),
+                        _t(g["rel"][rels], cuda_device), _t(indptr, cuda_device),
+                        _t(idx if len(idx) else np.zeros(1, np.int64), cuda_device))
+    for k in ("gt", "ge", "gt_f", "ge_f"):
+        assert np.array_equal(out[k].cpu().numpy(), g[k]), k
+    true = np.concatenate([heads, tails])
+    assert np.array_equal(out["true_score"].cpu().numpy(), g["pred"][np.arange(len(true)), true])
+    recip, hits = ops.metrics_from_counts(out["gt"], out["ge"], [1, 3, 10])
+    assert np.array_equal(recip.cpu().numpy(), g["recip"]) and np.array_equal(hits.cpu().numpy(), g["hits"])
+    recip, hits = ops.metrics_from_counts(out["gt_f"], out["ge_f"], [1, 3, 10])
+    assert np.array_equal(recip.cpu().numpy(), g["recip_f"]) and np.array_equal(hits.cpu().numpy(), g["hits_f"])
+    sums = ops.metrics_reduce(out["gt"], out["ge"], [1, 3, 10]).cpu().numpy()
+    assert abs(sums[0] - g["recip"].astype(np.float64).sum()) < 1e-9
+    assert np.array_equal(sums[1:], g["hits"].sum(0).astype(np.float64))
+
+
+@pytest.mark.parametrize("name", EVAL)
+def test_golden_score_fn_and_get_metrics(name, cuda_device):
+    """The reference's own call sequence (train.py:141-153) through the drop-in functions."""
+    g = golden(name)
+    model = name.split("_")[1]
+    fn = getattr(blp_b200, model + "_score")
+    ent = _t(g["ent"], cuda_device)
+    heads, tails, rels = (_t(g[k], cuda_device) for k in ("heads", "tails", "rels"))
+    ent_emb = ent.unsqueeze(0)
+    head_embs, tail_embs = ent[heads], ent[tails]              # (B,1,D)
+    rel_embs = _t(g["rel"], cuda_device)[rels]
+    hp = fn(ent_emb, tail_embs, rel_embs)
+    tp = fn(head_embs, ent_emb, rel_embs)
+    pred = torch.cat((hp, tp))
+    assert np.array_equal(pred.cpu().numpy(), g["pred"])
+    true = torch.cat((heads, tails))
+    recip, hits = blp_b200.get_metrics(pred, true, torch.tensor([[1, 3, 10]], device=cuda_device))
+    assert recip.shape == (pred.shape[0], 1) and hits.dtype == torch.bool
+    assert np.array_equal(recip.cpu().numpy(), g["recip"]) and np.array_equal(hits.cpu().numpy(), g["hits"])
+    # filtered re-rank exactly as train.py:164-167 writes it
+    mask = _t(unpack_mask(g), cuda_device)
+    pred[mask] = pred.min() - 1.0
+    recip, hits = blp_b200.get_metrics(pred, true, torch.tensor([[1, 3, 10]], device=cuda_device))
+    assert np.array_equal(recip.cpu().numpy(), g["recip_f"]) and np.array_equal(hits.cpu().numpy(), g["hits_f"])
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("n,b", [(1, 1), (31, 2), (128, 64), (129, 65), (1000, 7), (14541, 64)])
+def test_sweep_vs_oracle_d128(model, n, b, cuda_device):
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=n * 7 + b)
+    if n > 40:
+        ent[n - 1] = ent[3]            # exact ties
+        heads[0] = 3
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy())
+    e = ent.to(cuda_device)
+    out = ops.eval_rank(model, e, e[heads.to(cuda_device)], e[tails.to(cuda_device)], rel[rels].to(cuda_device))
+    assert np.array_equal(out["true_score"].cpu().numpy(), co["true_score"])
+    assert np.array_equal(out["gt"].cpu().numpy(), co["gt"])
+    assert np.array_equal(out["ge"].cpu().numpy(), co["ge"])
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d", (2, 64, 100, 256, 300, 768))
+def test_generic_width_vs_oracle(model, d, cuda_device):
+    n, b = 203, 5
+    ent, rel, heads, tails, rels = make_inputs(model, n, d, b, seed=d)
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy(), want_scores=True)
+    e = ent.to(cuda_device)
+    out = ops.eval_rank(model, e, e[heads.to(cuda_device)], e[tails.to(cuda_device)], rel[rels].to(cuda_device))
+    assert np.array_equal(out["true_score"].cpu().numpy(), co["true_score"])
+    assert np.array_equal(out["gt"].cpu().numpy(), co["gt"]) and np.array_equal(out["ge"].cpu().numpy(), co["ge"])
+    fn = getattr(blp_b200, model + "_score")
+    r = rel[rels].to(cuda_device).unsqueeze(1)
+    hp = fn(e.unsqueeze(0), e[tails.to(cuda_device)].unsqueeze(1), r)
+    tp = fn(e[heads.to(cuda_device)].unsqueeze(1), e.unsqueeze(0), r)
+    assert np.array_equal(torch.cat((hp, tp)).cpu().numpy(), co["scores"])
+
+
+def test_odd_width_rejected_for_halves_models(cuda_device):
+    x = torch.zeros(2, 1, 7, device=cuda_device)
+    for name in ("complex_score", "simple_score"):
+        with pytest.raises(ValueError):
+            getattr(blp_b200, name)(x, x, x)
+
+
+def test_empty_inputs(cuda_device):
+    ent = torch.randn(10, 128, device=cuda_device)
+    empty = torch.empty(0, 128, device=cuda_device)
+    out = ops.eval_rank("transe", ent, empty, empty, empty)
+    assert out["gt"].numel() == 0
+    q = torch.randn(3, 128, device=cuda_device)
+    out = ops.eval_rank("distmult", torch.empty(0, 128, device=cuda_device), q, q, q)
+    assert out["gt"].tolist() == [0] * 6 and out["ge"].tolist() == [0] * 6
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_shard_sums_equal_full_table(model, cuda_device):
+    """Integer counters add across row shards: any partition gives identical ranks."""
+    n, b = 5000, 40
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=99)
+    e = ent.to(cuda_device)
+    h, t, r = e[heads.to(cuda_device)], e[tails.to(cuda_device)], rel[rels].to(cuda_device)
+    mask = torch.rand(2 * b, n) < 0.02
+    mask[torch.arange(2 * b), torch.cat([heads, tails])] = False
+    indptr, idx = mask_to_csr(mask.numpy())
+    ip, ix = _t(indptr, cuda_device), _t(idx, cuda_device)
+    full = ops.eval_rank(model, e, h, t, r, ip, ix)
+    for world in (2, 3, 8):
+        acc = {k: torch.zeros_like(full[k]) for k in ("gt", "ge", "gt_f", "ge_f")}
+        for rank in range(world):
+            lo, hi = blp_b200.shard_bounds(n, world, rank)
+            part = ops.eval_rank(model, e[lo:hi], h, t, r, ip, ix, ent_offset=lo)
+            assert torch.equal(part["true_score"], full["true_score"])
+            for k in acc:
+                acc[k] += part[k]
+        for k in acc:
+            assert torch.equal(acc[k], full[k]), (k, world)
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy(), indptr, idx)
+    for k in ("gt", "ge", "gt_f", "ge_f"):
+        assert np.array_equal(full[k].cpu().numpy(), co[k]), k
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_rank_sweep_reproduces_reference_eval_loop(model, cuda_device):
+    """train.py:57-243 end to end (golden eval_loop_*): raw + filtered MRR and hits@k."""
+    g = golden("eval_loop_" + model)
+    ent2idx = blp_b200.make_ent2idx(torch.from_numpy(g["entities"]), int(g["n_ids"]) - 1)
+    triples = torch.from_numpy(g["triples"])
+    rows = torch.stack([ent2idx[triples[:, 0]], ent2idx[triples[:, 1]], triples[:, 2]], dim=1)
+    fidx = blp_b200.TripleFilterIndex(g["graph_edges"], ent2idx)
+    out = blp_b200.rank_sweep(model, _t(g["ent_emb"], cuda_device), _t(g["rel_weight"], cuda_device),
+                              rows.to(cuda_device), filter_index=fidx, filter_triples=g["triples"], chunk=40)
+    m = blp_b200.finalize(out)
+    want = dict(zip(g["scalar_names"].tolist(), g["scalar_values"].tolist()))
+    assert abs(m["mrr"] - want["test_mrr"]) <= 1e-6 and abs(m["mrr_f"] - want["test_mrr_filt"]) <= 1e-6
+    for j, k in enumerate((1, 3, 10)):
+        assert abs(m["hits_at_k"][j] - want[f"test_hits@{k}"]) <= 1e-9
+        assert abs(m["hits_at_k_f"][j] - want[f"test_hits@{k}_filt"]) <= 1e-9
+
+
+def test_full_size_properties_fb15k237(cuda_device):
+    """BASELINE config 2 at full size (N=14,541, 2,048 triples): size-independent checks.
+    (1) shard sums == full table; (2) permuting candidate rows leaves every rank unchanged;
+    (3) gt < ge (the true entity always ties itself); (4) a sampled subset of queries equals the oracle."""
+    model, n, b = "transe", 14541, 2048
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=5, n_rel=237)
+    e = ent.to(cuda_device)
+    hd, td = heads.to(cuda_device), tails.to(cuda_device)
+    r = rel[rels].to(cuda_device)
+    full = ops.eval_rank(model, e, e[hd], e[td], r)
+    assert bool((full["gt"] < full["ge"]).all())
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    shuffled = ops.eval_rank(model, e[perm], e[hd], e[td], r)
+    assert torch.equal(shuffled["gt"], full["gt"]) and torch.equal(shuffled["ge"], full["ge"])
+    lo, hi = blp_b200.shard_bounds(n, 2, 1)
+    a = ops.eval_rank(model, e[:lo], e[hd], e[td], r)
+    c = ops.eval_rank(model, e[lo:hi], e[hd], e[td], r, ent_offset=lo)
+    assert torch.equal(a["gt"] + c["gt"], full["gt"]) and torch.equal(a["ge"] + c["ge"], full["ge"])
+    sel = torch.arange(0, b, 64)
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads[sel]].numpy(), ent[tails[sel]].numpy(),
+                            rel[rels[sel]].numpy(), heads[sel].numpy(), tails[sel].numpy())
+    qsel = torch.cat([sel, sel + b])
+    assert np.array_equal(full["gt"].cpu()[qsel].numpy(), co["gt"])
+    assert np.array_equal(full["ge"].cpu()[qsel].numpy(), co["ge"])

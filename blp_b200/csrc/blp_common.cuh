@@ -34,6 +34,49 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2) -----------------------------
+// One 64-bit register pair holds the same quantity for TWO queries; add / sub /
+// mul round each half exactly like the scalar __f*_rn forms (no contraction), so
+// packing changes no bits.  A packed instruction takes one issue slot for two
+// lane-operations, which moves the exact-order sweeps from issue-bound to
+// FP32-pipe-bound.  ptxas folds abs2 / dup2 into operand modifiers (|R|, R.F32).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 dup2(float a) { return pack2(a, a); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Packed multiply, rounded once per half.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// with --fmad=false (CUDA 12.9), which would change bits, so the product is issued as fma(a, b, -0):
+// a*b + (-0) rounds to exactly fl(a*b) (including the sign of zero products), costs the same FFMA2 slot,
+// and an fma result cannot be folded into a following add.  `nz` must be the pair {-0.0f, -0.0f} taken
+// from a kernel argument (kNegZero2) so that ptxas cannot see its value and simplify the addend away.
+constexpr f2 kNegZero2 = 0x8000000080000000ull;
+__device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+__device__ __forceinline__ f2 abs2(f2 a) {
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return pack2(fabsf(lo), fabsf(hi));
+}
+
 // ---- one product term of the bilinear models, natural row layout ------------
 // models.py:226-227 / :230-239 / :242-248; j indexes [0, L), L = d (distmult)
 // or d/2 (complex, simple).

@@ -1,0 +1,568 @@
+// blp_sweep.cu -- the fused full-entity scoring + rank-counting kernel (a1-a4, a10, a11).
+//
+// Replaces train.py:141-157 + utils.py:103-105 for d == 128 (the width of every BLP script): for every
+// query (a test triple with its head or its tail removed) score ALL candidate entity rows and reduce the
+// scores to two integers, gt = #{s_j > s_true} and ge = #{s_j >= s_true}.  Neither the (B, N, D)
+// broadcast nor the (2B, N) score matrix is materialised.
+//
+// Layout
+//   - PERSISTENT grid, one CTA per SM, 8 consumer warps + 1 producer warp.  The work is the list of
+//     (triple group, candidate tile) pairs split evenly over the CTAs; a CTA crosses at most a few group
+//     boundaries and re-folds its queries at each.
+//   - a triple group carries BOTH roles: every consumer thread predicts the heads of its triples (the
+//     candidate row plays `heads`, train.py:146) with half of its query pairs and their tails
+//     (train.py:147) with the other half, so all warps do identical work, consume tiles in step, and each
+//     candidate tile is fetched once for both roles.
+//   - a slot is the 2 * TQP queries of one warp; a consumer thread owns a (TQP query pairs) x (TC
+//     candidates) register tile.  Large batches use TQP = 4, TC = 4 (32 triples = 64 queries per group,
+//     every warp covers all 128 tile rows).  Small batches (the reference's Wikidata5M eval_batch_size = 2) shrink
+//     TQP / TC and split the tile rows over 4 / TC warps per slot instead, so no lane-ops are spent on
+//     padding queries and the kernel becomes HBM bound.
+//   - query rows (h, t, r) are folded into <= 2 operand vectors per query (e.g. u = fl(h + r) for TransE
+//     tail prediction), stored in shared memory in *processing order*, interleaved in PAIRS of queries so
+//     one 64-bit register pair feeds a packed FADD2 / FFMA2 (two queries per issue slot);
+//   - candidate tiles (128 rows) are multi-buffered in shared memory with a 132-float pitch, so a lane
+//     that walks one row with 128-bit loads never conflicts; the producer warp fills them either with
+//     TMA bulk copies (natural order: TransE) or with coalesced 128-bit global loads + a permuting store
+//     (ATen sum order: DistMult / ComplEx / SimplE); mbarrier full / empty pairs per buffer;
+//   - every (query, candidate) replays the reference's exact fp32 operation order
+//     and is compared against the true-triple score.
+// The kernel is FP32-pipe bound for full groups (2-3 lane-ops per (query, candidate, dim) against 4/Q
+// bytes) and HBM bound for the small-batch shapes; see DESIGN.md.
+#include "blp_sweep.h"
+
+namespace blp {
+
+constexpr int kPitch = 132;                   // smem row pitch (floats)
+constexpr int kCW = 8;                        // consumer warps
+constexpr int kCT = 128;                      // candidate rows per tile
+constexpr int kThreads = (kCW + 1) * 32;
+constexpr int kSmemBudget = 227 * 1024 - 1024;
+
+template <int TQP_, int TC_>
+struct Cfg {
+    static constexpr int TQP = TQP_;          // query pairs per consumer thread
+    static constexpr int TC = TC_;            // candidates per consumer thread
+    static constexpr int RS = 4 / TC_;        // warps that share one slot (they split the 128 tile rows)
+    static constexpr int NS = kCW / RS;       // slots per CTA
+    static constexpr int SQ = 2 * TQP_;       // queries per slot
+    static constexpr int NQ = NS * SQ;        // queries per CTA
+    static constexpr int QV_BYTES = NS * TQP_ * 2 * kD * 2 * 4;
+    static constexpr int TILE_BYTES = kCT * kPitch * 4;
+    static constexpr int ST = (QV_BYTES + 3 * TILE_BYTES <= kSmemBudget) ? 3 : 2;   // tile buffers
+};
+
+template <class C>
+struct __align__(16) SweepSmem {
+    float qv[C::NS * C::TQP][2][kD][2];       // [query pair][operand vector][position][half], processing order
+    float ctile[C::ST][kCT][kPitch];          // candidate tiles, processing order
+    float st[C::NQ];                          // true-triple scores of the current group's queries
+    uint64_t full_bar[C::ST];
+    uint64_t empty_bar[C::ST];
+};
+
+// position of natural element j inside a staged row
+template <int MODEL>
+__host__ __device__ __forceinline__ constexpr int perm_pos(int j) {
+    if (MODEL == BLP_MODEL_TRANSE) return j;
+    if (MODEL == BLP_MODEL_DISTMULT) return (j & 7) * 16 + ((j >> 3) & 3) * 4 + (j >> 5);
+    return (j >> 6) * 64 + (j & 7) * 8 + ((j >> 3) & 3) * 2 + ((j & 63) >> 5);
+}
+
+// ---- query-side folding -----------------------------------------------------
+// HEAD_PRED: the candidate row plays `heads` (train.py:146); otherwise `tails` (train.py:147).
+// qp points at qv[pair][0][0][half]; operand vector v, position pos live at qp[(v * kD + pos) * 2].
+template <int MODEL, bool HEAD_PRED>
+__device__ __forceinline__ void fold_query(const float *__restrict__ h, const float *__restrict__ t,
+                                           const float *__restrict__ r, int j, float *__restrict__ qp) {
+    const int p = perm_pos<MODEL>(j);
+    auto put = [&](int v, int pos, float x) { qp[(v * kD + pos) * 2] = x; };
+    if (MODEL == BLP_MODEL_TRANSE || MODEL == BLP_MODEL_DISTMULT) {
+        if (HEAD_PRED) {
+            put(0, p, r[j]);
+            put(1, p, t[j]);
+        } else {
+            put(0, p, (MODEL == BLP_MODEL_TRANSE) ? fadd(h[j], r[j]) : fmul(h[j], r[j]));
+            put(1, p, 0.0f);
+        }
+    } else if (MODEL == BLP_MODEL_COMPLEX) {
+        if (HEAD_PRED) {
+            put(0, p, r[j]);
+            put(1, p, t[j]);
+        } else if (j < 64) {
+            const float hr = h[j], hi = h[64 + j], rr = r[j], ri = r[64 + j];
+            put(0, p, fmul(rr, hr));        // A
+            put(0, 64 + p, fmul(rr, hi));   // B
+            put(1, p, fmul(ri, hr));        // C
+            put(1, 64 + p, fmul(ri, hi));   // D
+        }
+    } else {  // SIMPLE
+        if (j < 64) {
+            if (HEAD_PRED) {             // candidate = (hh, ht)
+                put(0, p, r[j]);                          // ra
+                put(0, 64 + p, t[64 + j]);                // tt
+                put(1, p, fmul(t[j], r[64 + j]));         // th * rb
+                put(1, 64 + p, 0.0f);
+            } else {                     // candidate = (th, tt)
+                put(0, p, fmul(h[j], r[j]));              // hh * ra
+                put(0, 64 + p, r[64 + j]);                // rb
+                put(1, p, h[64 + j]);                     // ht
+                put(1, 64 + p, 0.0f);
+            }
+        }
+    }
+}
+
+// ---- per-position arithmetic on query PAIRS (f2 = two queries, same candidate) ----
+__device__ __forceinline__ f2 transe_step(bool HEAD_PRED, f2 acc, float e, f2 v0, f2 v1) {
+    const f2 x = HEAD_PRED ? sub2(add2(dup2(e), v0), v1) : sub2(v0, dup2(e));
+    return add2(acc, abs2(x));
+}
+__device__ __forceinline__ f2 distmult_term(bool HEAD_PRED, float e, f2 v0, f2 v1, f2 nz) {
+    return HEAD_PRED ? mul2(mul2(dup2(e), v0, nz), v1, nz) : mul2(v0, dup2(e), nz);
+}
+template <int MODEL>
+__device__ __forceinline__ f2 halves_term(bool HEAD_PRED, float elo_, float ehi_, f2 v0lo, f2 v0hi, f2 v1lo, f2 v1hi, f2 nz) {
+    const f2 elo = dup2(elo_), ehi = dup2(ehi_);
+    if (MODEL == BLP_MODEL_COMPLEX) {
+        if (HEAD_PRED) {  // e = (hr, hi); v0 = (rr, ri); v1 = (tr, ti)
+            f2 p = add2(mul2(mul2(v0lo, elo, nz), v1lo, nz), mul2(mul2(v0lo, ehi, nz), v1hi, nz));
+            p = add2(p, mul2(mul2(v0hi, elo, nz), v1hi, nz));
+            return sub2(p, mul2(mul2(v0hi, ehi, nz), v1lo, nz));
+        } else {          // e = (tr, ti); v0 = (A, B); v1 = (C, D)
+            f2 p = add2(mul2(v0lo, elo, nz), mul2(v0hi, ehi, nz));
+            p = add2(p, mul2(v1lo, ehi, nz));
+            return sub2(p, mul2(v1hi, elo, nz));
+        }
+    } else {
+        if (HEAD_PRED) return add2(mul2(mul2(elo, v0lo, nz), v0hi, nz), mul2(v1lo, ehi, nz));   // (hh*ra)*tt + (th*rb)*ht
+        return add2(mul2(v0lo, ehi, nz), mul2(mul2(elo, v0hi, nz), v1lo, nz));                  // (hh*ra)*tt + (th*rb)*ht
+    }
+}
+
+__device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// four consecutive staged positions of one operand vector of one query pair
+struct Q4 {
+    f2 x, y, z, w;
+};
+__device__ __forceinline__ Q4 ldq4(const float *qv, int q, int v, int off) {
+    const float *p = qv + ((q * 2 + v) * kD + off) * 2;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(p);
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(p + 4);
+    Q4 r;
+    r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+__device__ __forceinline__ Q4 q4_zero() {
+    Q4 r;
+    r.x = r.y = r.z = r.w = 0ull;
+    return r;
+}
+
+// role of query pair q inside a thread's register tile
+constexpr int kRoleHead = 0, kRoleTail = 1, kRoleMixed = 2;   // mixed: first half of the pairs head, second half tail
+template <int ROLE, int TQP>
+__host__ __device__ __forceinline__ constexpr bool pair_is_head(int q) {
+    return ROLE == kRoleHead || (ROLE == kRoleMixed && q < TQP / 2);
+}
+
+// Scores of a (TQP query pairs) x (TC candidates) register tile against the staged rows row0 + i * 32 * kPitch.
+// qv = this warp's first query pair.  On return s[q][i] holds the final bilinear scores of queries 2q, 2q+1,
+// or the L1 distance (the caller flips the sign) for TransE.  Loop nests are ordered (pair, position,
+// candidate) so consecutive packed instructions belong to different accumulation chains.
+template <int MODEL, int ROLE, int TQP, int TC>
+__device__ __forceinline__ void score_tile(const float *__restrict__ row0, const float *__restrict__ qv, f2 nz,
+                                           f2 (&s)[TQP][TC]) {
+#define HEAD_PRED (pair_is_head<ROLE, TQP>(q))
+#pragma unroll
+    for (int q = 0; q < TQP; ++q)
+#pragma unroll
+        for (int i = 0; i < TC; ++i) s[q][i] = 0ull;
+
+    if (MODEL == BLP_MODEL_TRANSE) {
+        // strictly sequential L1 accumulation, natural order
+#pragma unroll 2
+        for (int c4 = 0; c4 < kD / 4; ++c4) {
+            float e[TC][4];
+#pragma unroll
+            for (int i = 0; i < TC; ++i) {
+                const float4 v = lds128(row0 + i * 32 * kPitch + 4 * c4);
+                e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < TQP; ++q) {
+                const Q4 a = ldq4(qv, q, 0, 4 * c4);
+                const Q4 b = HEAD_PRED ? ldq4(qv, q, 1, 4 * c4) : q4_zero();
+                const f2 av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) s[q][i] = transe_step(HEAD_PRED, s[q][i], e[i][k], av[k], bv[k]);
+            }
+        }
+    } else if (MODEL == BLP_MODEL_DISTMULT) {
+        // staged order: pos = l*16 + a*4 + k  <->  j = 32k + 8a + l; one 16-byte chunk = one (l, a) chain
+        for (int l = 0; l < 8; ++l) {
+            f2 c[TQP][TC];
+#pragma unroll
+            for (int q = 0; q < TQP; ++q)
+#pragma unroll
+                for (int i = 0; i < TC; ++i) c[q][i] = 0ull;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int off = l * 16 + a * 4;
+                float e[TC][4];
+#pragma unroll
+                for (int i = 0; i < TC; ++i) {
+                    const float4 v = lds128(row0 + i * 32 * kPitch + off);
+                    e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < TQP; ++q) {
+                    const Q4 v0 = ldq4(qv, q, 0, off);
+                    const Q4 v1 = HEAD_PRED ? ldq4(qv, q, 1, off) : q4_zero();
+                    const f2 v0v[4] = {v0.x, v0.y, v0.z, v0.w}, v1v[4] = {v1.x, v1.y, v1.z, v1.w};
+                    f2 chain[TC];
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) chain[i] = distmult_term(HEAD_PRED, e[i][0], v0v[0], v1v[0], nz);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+#pragma unroll
+                        for (int i = 0; i < TC; ++i)
+                            chain[i] = add2(chain[i], distmult_term(HEAD_PRED, e[i][k], v0v[k], v1v[k], nz));
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) c[q][i] = add2(c[q][i], chain[i]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < TQP; ++q)
+#pragma unroll
+                for (int i = 0; i < TC; ++i) s[q][i] = add2(s[q][i], c[q][i]);
+        }
+    } else {
+        // halves; staged order per half: pos = l*8 + a*2 + k; one chunk = two (l, a) chains of length 2
+        for (int l = 0; l < 8; ++l) {
+            f2 c[TQP][TC];
+#pragma unroll
+            for (int q = 0; q < TQP; ++q)
+#pragma unroll
+                for (int i = 0; i < TC; ++i) c[q][i] = 0ull;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int off = l * 8 + hh * 4;
+                float4 elo[TC], ehi[TC];
+#pragma unroll
+                for (int i = 0; i < TC; ++i) {
+                    elo[i] = lds128(row0 + i * 32 * kPitch + off);
+                    ehi[i] = lds128(row0 + i * 32 * kPitch + 64 + off);
+                }
+#pragma unroll
+                for (int q = 0; q < TQP; ++q) {
+                    const Q4 v0lo = ldq4(qv, q, 0, off);
+                    const Q4 v0hi = ldq4(qv, q, 0, 64 + off);
+                    const Q4 v1lo = ldq4(qv, q, 1, off);
+                    const Q4 v1hi = (MODEL == BLP_MODEL_COMPLEX) ? ldq4(qv, q, 1, 64 + off) : q4_zero();
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) {
+                        const f2 p0 = halves_term<MODEL>(HEAD_PRED, elo[i].x, ehi[i].x, v0lo.x, v0hi.x, v1lo.x, v1hi.x, nz);
+                        const f2 p1 = halves_term<MODEL>(HEAD_PRED, elo[i].y, ehi[i].y, v0lo.y, v0hi.y, v1lo.y, v1hi.y, nz);
+                        const f2 p2 = halves_term<MODEL>(HEAD_PRED, elo[i].z, ehi[i].z, v0lo.z, v0hi.z, v1lo.z, v1hi.z, nz);
+                        const f2 p3 = halves_term<MODEL>(HEAD_PRED, elo[i].w, ehi[i].w, v0lo.w, v0hi.w, v1lo.w, v1hi.w, nz);
+                        const f2 cc = add2(c[q][i], add2(p0, p1));
+                        c[q][i] = add2(cc, add2(p2, p3));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < TQP; ++q)
+#pragma unroll
+                for (int i = 0; i < TC; ++i) s[q][i] = add2(s[q][i], c[q][i]);
+        }
+        if (MODEL == BLP_MODEL_SIMPLE) {
+#pragma unroll
+            for (int q = 0; q < TQP; ++q)
+#pragma unroll
+                for (int i = 0; i < TC; ++i) s[q][i] = mul2(s[q][i], dup2(0.5f), nz);
+        }
+    }
+}
+#undef HEAD_PRED
+
+__device__ __forceinline__ void consumer_bar_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory");
+}
+
+// How the queries of a triple group map onto slots (a slot = the SQ queries of one warp-set):
+//   ROLES == 3, TQP >= 2  "mixed": every slot takes TQP triples; its first TQP queries (pairs [0, TQP/2))
+//                          predict their heads, the other TQP queries predict the tails of the SAME triples,
+//                          so all warps do identical work and consume tiles in step;
+//   ROLES == 3, TQP == 1  "split": a thread holds one pair, so the first half of the slots predicts heads
+//                          and the second half tails (2 triples per group);
+//   ROLES == 1 / 2         single role (the score_fn fast path): every slot takes SQ triples.
+template <class C, int ROLES>
+struct QueryMap {
+    static constexpr bool kMixed = ROLES == 3 && C::TQP >= 2;
+    static constexpr bool kSplit = ROLES == 3 && C::TQP == 1;
+    static constexpr int kTriplesPerSlot = kMixed ? C::TQP : C::SQ;
+    static constexpr int kRoleSlots = kSplit ? C::NS / 2 : C::NS;
+    static constexpr int kTriplesPerGroup = kRoleSlots * kTriplesPerSlot;
+    __device__ static __forceinline__ bool is_head(int slot, int qi) {
+        if (kMixed) return qi < C::TQP;
+        if (kSplit) return slot < C::NS / 2;
+        return ROLES == 1;
+    }
+    __device__ static __forceinline__ int triple(int slot, int qi) {      // offset inside the group
+        if (kMixed) return slot * C::TQP + (qi % C::TQP);
+        if (kSplit) return (slot % (C::NS / 2)) * C::SQ + qi;
+        return slot * C::SQ + qi;
+    }
+};
+
+template <int MODEL, class C, int ROLES>
+__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args) {
+    using QM = QueryMap<C, ROLES>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SweepSmem<C> &sm = *reinterpret_cast<SweepSmem<C> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::ST; ++s) {
+            mbar_init(&sm.full_bar[s], 1);
+            mbar_init(&sm.empty_bar[s], kCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- this CTA's share of the (group, tile) list ---------------------------------------------
+    const long long ntiles = (args.n_local + kCT - 1) / kCT;
+    const long long total = ntiles * args.groups;
+    const long long id_begin = total * blockIdx.x / gridDim.x, id_end = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == kCW) {
+        // ===================== producer warp =====================
+        int it = 0;
+        for (long long id = id_begin; id < id_end; ++id, ++it) {
+            const long long tile = id % ntiles;
+            const int buf = it % C::ST;
+            const uint32_t use = (uint32_t)(it / C::ST);
+            mbar_wait(&sm.empty_bar[buf], (use & 1u) ^ 1u);
+            const long long base = tile * kCT;
+            const int rows = (int)min((long long)kCT, args.n_local - base);
+            float *dst = &sm.ctile[buf][0][0];
+            if (MODEL == BLP_MODEL_TRANSE && args.use_tma) {
+                if (lane == 0) mbar_arrive_expect_tx(&sm.full_bar[buf], (uint32_t)rows * kD * 4u);
+                __syncwarp();
+                for (int row = lane; row < rows; row += 32)
+                    tma_bulk_g2s(dst + row * kPitch, args.ent + (base + row) * kD, kD * 4u, &sm.full_bar[buf]);
+            } else {
+                // 16-byte chunks; a warp-wide load covers one 512-byte row
+#pragma unroll 1
+                for (int batch = 0; batch < kCT / 16; ++batch) {
+                    float4 v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int row = batch * 16 + u;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < rows) v[u] = __ldg(reinterpret_cast<const float4 *>(args.ent + (base + row) * kD) + lane);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        float *drow = dst + (batch * 16 + u) * kPitch;
+                        if (MODEL == BLP_MODEL_TRANSE) {
+                            *reinterpret_cast<float4 *>(drow + 4 * lane) = v[u];
+                        } else {
+                            drow[perm_pos<MODEL>(4 * lane + 0)] = v[u].x;
+                            drow[perm_pos<MODEL>(4 * lane + 1)] = v[u].y;
+                            drow[perm_pos<MODEL>(4 * lane + 2)] = v[u].z;
+                            drow[perm_pos<MODEL>(4 * lane + 3)] = v[u].w;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full_bar[buf]);
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    // RS warps share a slot and split the 128 tile rows between them
+    const int slot = warp / C::RS, rowgrp = warp % C::RS;
+    const float *qv = &sm.qv[slot * C::TQP][0][0][0];
+    const int row_off = rowgrp * C::TC * 32 + lane;                        // this lane's first row inside a tile
+    const long long tail_base = (ROLES == 3) ? args.b : 0;                 // tail queries follow the b head queries
+
+    int it = 0;
+    long long id = id_begin;
+    while (id < id_end) {
+        // ---- segment = the run of this CTA's tiles that belong to one triple group
+        const long long grp = id / ntiles;
+        const long long seg_end = min(id_end, (grp + 1) * ntiles);
+        const long long t0 = grp * QM::kTriplesPerGroup;                   // first triple of this group
+
+        consumer_bar_sync();                      // everyone is done with the previous group's vectors
+        for (int idx = tid; idx < C::NQ * kD; idx += kCW * 32) {
+            const int ql = idx >> 7, j = idx & (kD - 1);                   // ql = slot * SQ + query in slot
+            const int s_ = ql / C::SQ, qi = ql % C::SQ;
+            const bool hp = QM::is_head(s_, qi);
+            const long long tr = t0 + QM::triple(s_, qi);
+            float *qp = &sm.qv[ql >> 1][0][0][ql & 1];
+            if (tr < args.b) {
+                const float *h = args.h_rows + tr * kD, *t = args.t_rows + tr * kD, *r = args.r_rows + tr * kD;
+                if (hp) fold_query<MODEL, true>(h, t, r, j, qp);
+                else fold_query<MODEL, false>(h, t, r, j, qp);
+            } else {
+                qp[j * 2] = 0.0f;
+                qp[(kD + j) * 2] = 0.0f;
+            }
+        }
+        if (tid < C::NQ) {
+            const int s_ = tid / C::SQ, qi = tid % C::SQ;
+            const long long tr = t0 + QM::triple(s_, qi);
+            const long long qo = (QM::is_head(s_, qi) ? 0 : tail_base) + tr;
+            sm.st[tid] = (args.true_score && tr < args.b) ? args.true_score[qo] : 0.0f;
+        }
+        consumer_bar_sync();
+
+        float st[C::SQ];
+        long long qo[C::SQ];                      // output row of each of this thread's queries, -1 = padding
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < C::SQ; ++q) {
+            st[q] = sm.st[slot * C::SQ + q];
+            const long long tr = t0 + QM::triple(slot, q);
+            qo[q] = tr < args.b ? (QM::is_head(slot, q) ? 0 : tail_base) + tr : -1;
+            any |= qo[q] >= 0;
+        }
+        int cgt[C::SQ], cge[C::SQ];
+#pragma unroll
+        for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
+
+        for (; id < seg_end; ++id, ++it) {
+            const long long tile = id % ntiles;
+            const int buf = it % C::ST;
+            const uint32_t use = (uint32_t)(it / C::ST);
+            mbar_wait(&sm.full_bar[buf], use & 1u);
+            float s[C::SQ][C::TC];
+            if (any) {                            // warp-uniform: slots past the end of the batch have no queries
+                f2 sp[C::TQP][C::TC];
+                const float *row0 = &sm.ctile[buf][0][0] + row_off * kPitch;
+                if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
+                else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
+                else score_tile<MODEL, kRoleTail, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
+#pragma unroll
+                for (int q = 0; q < C::TQP; ++q)
+#pragma unroll
+                    for (int i = 0; i < C::TC; ++i) {
+                        unpack2(sp[q][i], s[2 * q][i], s[2 * q + 1][i]);
+                        if (MODEL == BLP_MODEL_TRANSE) {              // score = -||.||_1
+                            s[2 * q][i] = -s[2 * q][i];
+                            s[2 * q + 1][i] = -s[2 * q + 1][i];
+                        }
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty_bar[buf]);
+            if (!any) continue;
+
+            const long long base = tile * kCT + row_off;
+            if (args.scores_out) {
+#pragma unroll
+                for (int q = 0; q < C::SQ; ++q) {
+                    if (qo[q] >= 0) {
+#pragma unroll
+                        for (int i = 0; i < C::TC; ++i) {
+                            const long long cand = base + 32 * i;
+                            if (cand < args.n_local) args.scores_out[qo[q] * args.ld_scores + cand] = s[q][i];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < C::TC; ++i) {
+                    const bool valid = base + 32 * i < args.n_local;
+#pragma unroll
+                    for (int q = 0; q < C::SQ; ++q) {
+                        cgt[q] += (valid && s[q][i] > st[q]) ? 1 : 0;
+                        cge[q] += (valid && s[q][i] >= st[q]) ? 1 : 0;
+                    }
+                }
+            }
+        }
+        if (!args.scores_out) {
+#pragma unroll
+            for (int q = 0; q < C::SQ; ++q) {
+                const int a = __reduce_add_sync(0xffffffffu, cgt[q]);
+                const int c = __reduce_add_sync(0xffffffffu, cge[q]);
+                if (lane == 0 && qo[q] >= 0 && (a | c)) {
+                    atomicAdd(&args.gt[qo[q]], a);
+                    atomicAdd(&args.ge[qo[q]], c);
+                }
+            }
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------
+static int num_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+template <int MODEL, class C, int ROLES>
+static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
+    const size_t smem = sizeof(SweepSmem<C>);
+    BLP_CUDA(cudaFuncSetAttribute(sweep_kernel<MODEL, C, ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SweepArgs args = a;
+    const int tg = QueryMap<C, ROLES>::kTriplesPerGroup;
+    args.groups = (a.b + tg - 1) / tg;
+    const long long ntiles = (a.n_local + kCT - 1) / kCT;
+    const long long items = ntiles * args.groups;
+    if (items == 0) return BLP_OK;
+    const long long sms = num_sms();
+    const unsigned grid = (unsigned)(items < sms ? items : sms);
+    prof_begin(1, st);
+    sweep_kernel<MODEL, C, ROLES><<<grid, kThreads, smem, st>>>(args);
+    prof_end(1, st);
+    count_launch();
+    BLP_CUDA(cudaGetLastError());
+    return BLP_OK;
+}
+
+// Register-tile shape by batch size: the smallest slot that holds the batch without padding queries.
+// BLP_SWEEP_CFG=0..4 forces one (tuning aid).
+template <int MODEL>
+static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
+    if (a.roles == 1) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 1>(a, st);   // score_fn fast path: full tiles only
+    if (a.roles == 2) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 2>(a, st);
+    int cfg = a.b <= 2 ? 0 : a.b <= 4 ? 1 : a.b <= 8 ? 2 : a.b <= 16 ? 3 : 4;
+    const char *e = getenv("BLP_SWEEP_CFG");
+    if (e && e[0] >= '0' && e[0] <= '4') cfg = e[0] - '0';
+    switch (cfg) {
+    case 0: return launch_sweep_cfg<MODEL, Cfg<1, 1>, 3>(a, st);             //  2 triples / group (split roles)
+    case 1: return launch_sweep_cfg<MODEL, Cfg<2, 1>, 3>(a, st);             //  4
+    case 2: return launch_sweep_cfg<MODEL, Cfg<4, 1>, 3>(a, st);             //  8
+    case 3: return launch_sweep_cfg<MODEL, Cfg<4, 2>, 3>(a, st);             // 16
+    default: return launch_sweep_cfg<MODEL, Cfg<4, 4>, 3>(a, st);            // 32
+    }
+}
+
+int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st) {
+    switch (model) {
+    case BLP_MODEL_TRANSE: return launch_sweep<BLP_MODEL_TRANSE>(a, st);
+    case BLP_MODEL_DISTMULT: return launch_sweep<BLP_MODEL_DISTMULT>(a, st);
+    case BLP_MODEL_COMPLEX: return launch_sweep<BLP_MODEL_COMPLEX>(a, st);
+    default: return launch_sweep<BLP_MODEL_SIMPLE>(a, st);
+    }
+}
+
+int sweep_env_use_tma() {
+    const char *e = getenv("BLP_EVAL_PRODUCER");
+    if (e && (e[0] == 'l' || e[0] == 'L')) return 0;   // "ldg"
+    return 1;
+}
+
+}  // namespace blp

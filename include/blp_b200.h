@@ -162,8 +162,9 @@ int blp_l2_regularization(const float *heads, int64_t n_heads, const float *tail
  *   2 = add.f32x2       two chains per instruction
  *   3 = f32x2 TransE    {acc0,acc1} += |{u0,u1} - {e,e}|  (2 packed adds + 2 LOP)
  *   4 = FMUL + FADD     acc = acc + v * e     (the DistMult tail-pred step, unfused)
+ *   5 = f32x2 DistMult  {acc0,acc1} += {v0,v1} * {e,e}  (packed product as fma(a,b,-0) + packed add)
  * *lane_ops_host receives the number of fp32 lane operations issued (adds and
- * multiplies; the integer AND of variant 3 is not counted). */
+ * multiplies). */
 int blp_pipe_probe(int variant, float *sink, int64_t n_threads, int iters, double *lane_ops_host, void *stream);
 
 /* Bracket the dominant kernel of the following calls on THIS thread with the

@@ -82,7 +82,8 @@ def test_golden_score_fn_and_get_metrics(name, cuda_device):
 
 
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("n,b", [(1, 1), (31, 2), (128, 64), (129, 65), (1000, 7), (14541, 64)])
+@pytest.mark.parametrize("n,b", [(1, 1), (31, 2), (257, 3), (128, 64), (129, 65), (1000, 7), (777, 12), (300, 33),
+                                 (14541, 64)])
 def test_sweep_vs_oracle_d128(model, n, b, cuda_device):
     ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=n * 7 + b)
     if n > 40:

@@ -7,7 +7,7 @@ import torch  # noqa: E402
 
 from blp_b200 import ops  # noqa: E402
 
-NAMES = ["FADD", "FADD+|x| (TransE tail step)", "add.f32x2", "f32x2 TransE step (2 packed adds + LOP)", "FMUL+FADD (DistMult tail step)"]
+NAMES = ["FADD", "FADD+|x| (TransE tail step)", "add.f32x2", "f32x2 TransE step (2 packed adds + LOP)", "FMUL+FADD (DistMult tail step)", "f32x2 DistMult tail step (FFMA2 + FADD2)"]
 dev = torch.device("cuda", 0)
 for v, name in enumerate(NAMES):
     best = 0.0

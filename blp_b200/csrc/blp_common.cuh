@@ -220,4 +220,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
+// 2-D tiled tensor copy global -> shared (TMA, SASS UTMALDG): box origin (c0 = innermost coordinate, c1 = row)
+__device__ __forceinline__ void tma_tensor2d_g2s(void *dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 }  // namespace blp

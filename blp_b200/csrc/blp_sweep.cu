@@ -29,11 +29,14 @@
 //     and is compared against the true-triple score.
 // The kernel is FP32-pipe bound for full groups (2-3 lane-ops per (query, candidate, dim) against 4/Q
 // bytes) and HBM bound for the small-batch shapes; see DESIGN.md.
+#include <cuda.h>
+#include <string.h>
+
 #include "blp_sweep.h"
 
 namespace blp {
 
-constexpr int kPitch = 132;                   // smem row pitch (floats)
+constexpr int kPitch = 132;                   // smem row pitch (floats) of the padded (bilinear) tile layout
 constexpr int kCW = 8;                        // consumer warps
 constexpr int kCT = 128;                      // candidate rows per tile
 constexpr int kThreads = (kCW + 1) * 32;
@@ -48,17 +51,52 @@ struct Cfg {
     static constexpr int SQ = 2 * TQP_;       // queries per slot
     static constexpr int NQ = NS * SQ;        // queries per CTA
     static constexpr int QV_BYTES = NS * TQP_ * 2 * kD * 2 * 4;
-    static constexpr int TILE_BYTES = kCT * kPitch * 4;
-    static constexpr int ST = (QV_BYTES + 3 * TILE_BYTES <= kSmemBudget) ? 3 : 2;   // tile buffers
 };
 
-template <class C>
-struct __align__(16) SweepSmem {
+// Staged tile layouts (one lane walks one candidate row with 128-bit loads; both are conflict-free):
+//   TransE    natural element order, written by TMA tensor copies as four 32-float column blocks of
+//             [128 rows][32 floats] with the 128-byte swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7));
+//   bilinear  ATen sum order (perm_pos), written by the producer warp, rows padded to 132 floats.
+template <int MODEL>
+struct TileLayout {
+    static constexpr bool kSwizzled = MODEL == BLP_MODEL_TRANSE;
+    static constexpr int kFloats = kSwizzled ? kCT * kD : kCT * kPitch;
+    // 16-byte chunk holding staged positions [4 * pos4, 4 * pos4 + 4) of tile row `row`
+    __device__ static __forceinline__ int chunk(int row, int pos4) {
+        if (kSwizzled) return (pos4 >> 3) * (kCT * 32) + row * 32 + (((pos4 & 7) ^ (row & 7)) << 2);
+        return row * kPitch + 4 * pos4;
+    }
+};
+
+template <int MODEL, class C>
+struct Stages {
+    static constexpr int ST = (C::QV_BYTES + 3 * TileLayout<MODEL>::kFloats * 4 <= kSmemBudget) ? 3 : 2;   // tile buffers
+};
+
+template <int MODEL, class C>
+struct __align__(1024) SweepSmem {
+    static constexpr int ST = Stages<MODEL, C>::ST;
+    float ctile[ST][TileLayout<MODEL>::kFloats];   // candidate tiles (1024-byte aligned for the TMA swizzle)
     float qv[C::NS * C::TQP][2][kD][2];       // [query pair][operand vector][position][half], processing order
-    float ctile[C::ST][kCT][kPitch];          // candidate tiles, processing order
     float st[C::NQ];                          // true-triple scores of the current group's queries
-    uint64_t full_bar[C::ST];
-    uint64_t empty_bar[C::ST];
+    uint64_t full_bar[ST];
+    uint64_t empty_bar[ST];
+};
+
+// per-lane view of a staged tile: rows row + 32 * i, i < TC.  All of a lane's rows share row & 7, so the
+// swizzle is one XOR of the (compile-time) chunk index with a per-lane constant.
+template <int MODEL>
+struct TileView {
+    const float *lane_base;   // tile base + this lane's first row
+    int xr;                   // (row & 7) << 2 for the swizzled layout
+    __device__ __forceinline__ TileView(const float *tile, int row)
+        : lane_base(tile + (TileLayout<MODEL>::kSwizzled ? row * 32 : row * kPitch)), xr((row & 7) << 2) {}
+    // 16-byte chunk holding staged positions [4 * pos4, 4 * pos4 + 4) of row (row + 32 * i)
+    __device__ __forceinline__ float4 load(int i, int pos4) const {
+        if (TileLayout<MODEL>::kSwizzled)
+            return *reinterpret_cast<const float4 *>(lane_base + i * (32 * 32) + (pos4 >> 3) * (kCT * 32) + (((pos4 & 7) << 2) ^ xr));
+        return *reinterpret_cast<const float4 *>(lane_base + i * (32 * kPitch) + 4 * pos4);
+    }
 };
 
 // position of natural element j inside a staged row
@@ -167,12 +205,12 @@ __host__ __device__ __forceinline__ constexpr bool pair_is_head(int q) {
     return ROLE == kRoleHead || (ROLE == kRoleMixed && q < TQP / 2);
 }
 
-// Scores of a (TQP query pairs) x (TC candidates) register tile against the staged rows row0 + i * 32 * kPitch.
+// Scores of a (TQP query pairs) x (TC candidates) register tile against the staged rows tv.row + 32 * i.
 // qv = this warp's first query pair.  On return s[q][i] holds the final bilinear scores of queries 2q, 2q+1,
 // or the L1 distance (the caller flips the sign) for TransE.  Loop nests are ordered (pair, position,
 // candidate) so consecutive packed instructions belong to different accumulation chains.
 template <int MODEL, int ROLE, int TQP, int TC>
-__device__ __forceinline__ void score_tile(const float *__restrict__ row0, const float *__restrict__ qv, f2 nz,
+__device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float *__restrict__ qv, f2 nz,
                                            f2 (&s)[TQP][TC]) {
 #define HEAD_PRED (pair_is_head<ROLE, TQP>(q))
 #pragma unroll
@@ -182,12 +220,15 @@ __device__ __forceinline__ void score_tile(const float *__restrict__ row0, const
 
     if (MODEL == BLP_MODEL_TRANSE) {
         // strictly sequential L1 accumulation, natural order
-#pragma unroll 2
-        for (int c4 = 0; c4 < kD / 4; ++c4) {
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int c4 = cb * 8 + cc;
             float e[TC][4];
 #pragma unroll
             for (int i = 0; i < TC; ++i) {
-                const float4 v = lds128(row0 + i * 32 * kPitch + 4 * c4);
+                const float4 v = tv.load(i, c4);
                 e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
             }
 #pragma unroll
@@ -215,7 +256,7 @@ __device__ __forceinline__ void score_tile(const float *__restrict__ row0, const
                 float e[TC][4];
 #pragma unroll
                 for (int i = 0; i < TC; ++i) {
-                    const float4 v = lds128(row0 + i * 32 * kPitch + off);
+                    const float4 v = tv.load(i, off >> 2);
                     e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
                 }
 #pragma unroll
@@ -254,8 +295,8 @@ __device__ __forceinline__ void score_tile(const float *__restrict__ row0, const
                 float4 elo[TC], ehi[TC];
 #pragma unroll
                 for (int i = 0; i < TC; ++i) {
-                    elo[i] = lds128(row0 + i * 32 * kPitch + off);
-                    ehi[i] = lds128(row0 + i * 32 * kPitch + 64 + off);
+                    elo[i] = tv.load(i, off >> 2);
+                    ehi[i] = tv.load(i, (off >> 2) + 16);
                 }
 #pragma unroll
                 for (int q = 0; q < TQP; ++q) {
@@ -320,14 +361,16 @@ struct QueryMap {
 };
 
 template <int MODEL, class C, int ROLES>
-__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args) {
+__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args, const __grid_constant__ CUtensorMap tmap) {
     using QM = QueryMap<C, ROLES>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SweepSmem<C> &sm = *reinterpret_cast<SweepSmem<C> *>(smem_raw);
+    using SM = SweepSmem<MODEL, C>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the TMA swizzle; plain pointer arithmetic keeps the shared address space (LDS, not LD)
+    SM &sm = *reinterpret_cast<SM *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < C::ST; ++s) {
+        for (int s = 0; s < SM::ST; ++s) {
             mbar_init(&sm.full_bar[s], 1);
             mbar_init(&sm.empty_bar[s], kCW);
         }
@@ -345,17 +388,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         int it = 0;
         for (long long id = id_begin; id < id_end; ++id, ++it) {
             const long long tile = id % ntiles;
-            const int buf = it % C::ST;
-            const uint32_t use = (uint32_t)(it / C::ST);
+            const int buf = it % SM::ST;
+            const uint32_t use = (uint32_t)(it / SM::ST);
             mbar_wait(&sm.empty_bar[buf], (use & 1u) ^ 1u);
             const long long base = tile * kCT;
             const int rows = (int)min((long long)kCT, args.n_local - base);
-            float *dst = &sm.ctile[buf][0][0];
+            float *dst = &sm.ctile[buf][0];
             if (MODEL == BLP_MODEL_TRANSE && args.use_tma) {
-                if (lane == 0) mbar_arrive_expect_tx(&sm.full_bar[buf], (uint32_t)rows * kD * 4u);
-                __syncwarp();
-                for (int row = lane; row < rows; row += 32)
-                    tma_bulk_g2s(dst + row * kPitch, args.ent + (base + row) * kD, kD * 4u, &sm.full_bar[buf]);
+                // four tensor copies of [128 rows][32 floats]; rows past the end of the table arrive as zeros
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&sm.full_bar[buf], (uint32_t)(kCT * kD * 4));
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_tensor2d_g2s(dst + cb * (kCT * 32), &tmap, cb * 32, (int)base, &sm.full_bar[buf]);
+                }
             } else {
                 // 16-byte chunks; a warp-wide load covers one 512-byte row
 #pragma unroll 1
@@ -369,10 +415,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
                     }
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        float *drow = dst + (batch * 16 + u) * kPitch;
+                        const int row = batch * 16 + u;
                         if (MODEL == BLP_MODEL_TRANSE) {
-                            *reinterpret_cast<float4 *>(drow + 4 * lane) = v[u];
+                            *reinterpret_cast<float4 *>(dst + TileLayout<MODEL>::chunk(row, lane)) = v[u];
                         } else {
+                            float *drow = dst + row * kPitch;
                             drow[perm_pos<MODEL>(4 * lane + 0)] = v[u].x;
                             drow[perm_pos<MODEL>(4 * lane + 1)] = v[u].y;
                             drow[perm_pos<MODEL>(4 * lane + 2)] = v[u].z;
@@ -442,16 +489,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 
         for (; id < seg_end; ++id, ++it) {
             const long long tile = id % ntiles;
-            const int buf = it % C::ST;
-            const uint32_t use = (uint32_t)(it / C::ST);
+            const int buf = it % SM::ST;
+            const uint32_t use = (uint32_t)(it / SM::ST);
             mbar_wait(&sm.full_bar[buf], use & 1u);
             float s[C::SQ][C::TC];
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
-                const float *row0 = &sm.ctile[buf][0][0] + row_off * kPitch;
-                if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
-                else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
-                else score_tile<MODEL, kRoleTail, C::TQP, C::TC>(row0, qv, args.negzero2, sp);
+                const TileView<MODEL> tv(&sm.ctile[buf][0], row_off);
+                if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
+                else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
+                else score_tile<MODEL, kRoleTail, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
 #pragma unroll
                 for (int q = 0; q < C::TQP; ++q)
 #pragma unroll
@@ -512,9 +559,38 @@ static int num_sms() {
     return n > 0 ? n : 148;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D view of the table shard: [n_local rows][128 floats], boxes of [128 rows][32 floats], 128-byte swizzle
+static bool make_table_tmap(CUtensorMap *tm, const float *ent, long long n_local) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)n_local};
+    const cuuint64_t strides[1] = {(cuuint64_t)kD * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kCT};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ent), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODEL, class C, int ROLES>
 static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
-    const size_t smem = sizeof(SweepSmem<C>);
+    const size_t smem = sizeof(SweepSmem<MODEL, C>) + 1024;
     BLP_CUDA(cudaFuncSetAttribute(sweep_kernel<MODEL, C, ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SweepArgs args = a;
     const int tg = QueryMap<C, ROLES>::kTriplesPerGroup;
@@ -524,8 +600,11 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     if (items == 0) return BLP_OK;
     const long long sms = num_sms();
     const unsigned grid = (unsigned)(items < sms ? items : sms);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (MODEL == BLP_MODEL_TRANSE && args.use_tma && !make_table_tmap(&tmap, a.ent, a.n_local)) args.use_tma = 0;
     prof_begin(1, st);
-    sweep_kernel<MODEL, C, ROLES><<<grid, kThreads, smem, st>>>(args);
+    sweep_kernel<MODEL, C, ROLES><<<grid, kThreads, smem, st>>>(args, tmap);
     prof_end(1, st);
     count_launch();
     BLP_CUDA(cudaGetLastError());

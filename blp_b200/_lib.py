@@ -26,6 +26,9 @@ SYMBOLS = {
     "blp_metrics_from_counts": (_i32, [_vp, _vp, _i64, ctypes.POINTER(_i64), _i32, _vp, _vp, _vp]),
     "blp_metrics_reduce": (_i32, [_vp, _vp, _i64, ctypes.POINTER(_i64), _i32, _vp, _vp]),
     "blp_eval_rank": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_rank_sweep": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
+                              _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_rank_metrics": (_i32, [_vp, _vp, _i64, ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp]),
     "blp_train_workspace_bytes": (_i64, [_i64, _i64]),
     "blp_train_loss": (_i32, [_i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _f32,
                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

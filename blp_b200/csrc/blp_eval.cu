@@ -19,16 +19,15 @@ namespace blp {
 // replays the reference's sequential / ATen-order reduction from there (the same
 // score_exact code every other exact path uses, so all of them agree bit for bit).
 constexpr int kTrueWarps = 4;
-__global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, const float *__restrict__ h_rows,
-                                                                    const float *__restrict__ t_rows,
-                                                                    const float *__restrict__ r_rows, long long b, int d,
-                                                                    int staged, float *__restrict__ true_score,
+__global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, const RowRef hr, const RowRef tr,
+                                                                    const RowRef rr, long long b, long long tail_off,
+                                                                    int d, int staged, float *__restrict__ true_score,
                                                                     int *__restrict__ gt, int *__restrict__ ge) {
     extern __shared__ float ts_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i = (long long)blockIdx.x * kTrueWarps + warp;
     if (i >= b) return;
-    const float *h = h_rows + i * d, *t = t_rows + i * d, *r = r_rows + i * d;
+    const float *h = hr.row(i, d), *t = tr.row(i, d), *r = rr.row(i, d);
     if (staged) {
         float *sh = ts_smem + (size_t)warp * 3 * d, *stt = sh + d, *sr = stt + d;
         for (int j = lane; j < d; j += 32) {
@@ -40,11 +39,14 @@ __global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, 
         h = sh; t = stt; r = sr;
     }
     if (lane == 0) {
-        const float s = score_exact_dyn(model, h, t, r, d);
+        float s = score_exact_dyn(model, h, t, r, d);
+        // an index outside the table (train.py:137-138 asserts this never happens): NaN compares false
+        // against every candidate, so the query reports gt = ge = 0 and is detectable
+        if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
         true_score[i] = s;
-        true_score[b + i] = s;
-        gt[i] = 0; gt[b + i] = 0;
-        ge[i] = 0; ge[b + i] = 0;
+        true_score[tail_off + i] = s;
+        gt[i] = 0; gt[tail_off + i] = 0;
+        ge[i] = 0; ge[tail_off + i] = 0;
     }
 }
 
@@ -52,25 +54,26 @@ __global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, 
 // One warp per query: re-score the query's filtered candidates that live in this
 // shard and remove their contribution from the raw counts.
 __global__ void filter_correct_kernel(int model, const float *__restrict__ ent, long long n_local, long long ent_offset,
-                                      int d, const float *__restrict__ h_rows, const float *__restrict__ t_rows,
-                                      const float *__restrict__ r_rows, long long b,
-                                      const long long *__restrict__ indptr, const long long *__restrict__ idx,
-                                      const float *__restrict__ true_score, const int *__restrict__ gt,
-                                      const int *__restrict__ ge, int *__restrict__ gt_f, int *__restrict__ ge_f) {
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                      int d, const RowRef hr, const RowRef tr, const RowRef rr, long long b,
+                                      long long tail_off, const long long *__restrict__ indptr,
+                                      const long long *__restrict__ idx, const float *__restrict__ true_score,
+                                      const int *__restrict__ gt, const int *__restrict__ ge, int *__restrict__ gt_f,
+                                      int *__restrict__ ge_f) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // CSR row: heads then tails
     const int lane = threadIdx.x & 31;
     if (q >= 2 * b) return;
     const bool head_pred = q < b;
     const long long i = head_pred ? q : q - b;
-    const float st = true_score[q];
+    const long long o = head_pred ? i : tail_off + i;                               // output slot
+    const float st = true_score[o];
     int cg = 0, ce = 0;
     if (indptr) {
+        const float *h = hr.row(i, d), *t = tr.row(i, d), *r = rr.row(i, d);
         for (long long p = indptr[q] + lane; p < indptr[q + 1]; p += 32) {
             const long long row = idx[p] - ent_offset;
             if (row < 0 || row >= n_local) continue;
             const float *e = ent + row * d;
-            const float s = head_pred ? score_exact_dyn(model, e, t_rows + i * d, r_rows + i * d, d)
-                                      : score_exact_dyn(model, h_rows + i * d, e, r_rows + i * d, d);
+            const float s = head_pred ? score_exact_dyn(model, e, t, r, d) : score_exact_dyn(model, h, e, r, d);
             cg += s > st;
             ce += s >= st;
         }
@@ -78,33 +81,34 @@ __global__ void filter_correct_kernel(int model, const float *__restrict__ ent, 
     cg = __reduce_add_sync(0xffffffffu, cg);
     ce = __reduce_add_sync(0xffffffffu, ce);
     if (lane == 0) {
-        gt_f[q] = gt[q] - cg;
-        ge_f[q] = ge[q] - ce;
+        gt_f[o] = gt[o] - cg;
+        ge_f[o] = ge[o] - ce;
     }
 }
 
 // ---- generic-width sweep (d != 128): one thread per (query, candidate) -----
-__global__ void sweep_generic_kernel(int model, const float *__restrict__ ent, long long n_local, int d,
-                                     const float *__restrict__ h_rows, const float *__restrict__ t_rows,
-                                     const float *__restrict__ r_rows, long long b,
+__global__ void sweep_generic_kernel(int model, const float *__restrict__ ent, long long n_local, int d, const RowRef hr,
+                                     const RowRef tr, const RowRef rr, long long b, long long tail_off,
                                      const float *__restrict__ true_score, int *__restrict__ gt, int *__restrict__ ge) {
-    const long long q = blockIdx.y;
-    const bool head_pred = q < b;
-    const long long i = head_pred ? q : q - b;
-    const float st = true_score[q];
-    int cg = 0, ce = 0;
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_local; c += (long long)gridDim.x * blockDim.x) {
-        const float *e = ent + c * d;
-        const float s = head_pred ? score_exact_dyn(model, e, t_rows + i * d, r_rows + i * d, d)
-                                  : score_exact_dyn(model, h_rows + i * d, e, r_rows + i * d, d);
-        cg += s > st;
-        ce += s >= st;
-    }
-    cg = __reduce_add_sync(0xffffffffu, cg);
-    ce = __reduce_add_sync(0xffffffffu, ce);
-    if ((threadIdx.x & 31) == 0 && (cg | ce)) {
-        atomicAdd(&gt[q], cg);
-        atomicAdd(&ge[q], ce);
+    for (long long q = blockIdx.y; q < 2 * b; q += gridDim.y) {
+        const bool head_pred = q < b;
+        const long long i = head_pred ? q : q - b;
+        const long long o = head_pred ? i : tail_off + i;
+        const float st = true_score[o];
+        const float *h = hr.row(i, d), *t = tr.row(i, d), *r = rr.row(i, d);
+        int cg = 0, ce = 0;
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_local; c += (long long)gridDim.x * blockDim.x) {
+            const float *e = ent + c * d;
+            const float s = head_pred ? score_exact_dyn(model, e, t, r, d) : score_exact_dyn(model, h, e, r, d);
+            cg += s > st;
+            ce += s >= st;
+        }
+        cg = __reduce_add_sync(0xffffffffu, cg);
+        ce = __reduce_add_sync(0xffffffffu, ce);
+        if ((threadIdx.x & 31) == 0 && (cg | ce)) {
+            atomicAdd(&gt[o], cg);
+            atomicAdd(&ge[o], ce);
+        }
     }
 }
 
@@ -161,17 +165,24 @@ __global__ void metrics_kernel(const int *__restrict__ gt, const int *__restrict
 // train.py:154-157 accumulators: sums[0] = sum of reciprocal ranks, sums[1 + j] = number of hits at k_j.
 // One CTA, fp64 accumulation in a fixed order (deterministic).
 __global__ void __launch_bounds__(1024) metrics_reduce_kernel(const int *__restrict__ gt, const int *__restrict__ ge,
-                                                              long long q, KValues kv, double *__restrict__ sums) {
+                                                              long long q, KValues kv, float *__restrict__ recip,
+                                                              unsigned char *__restrict__ hits, double *__restrict__ sums) {
     __shared__ double scratch[32][9];
     double acc[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) acc[j] = 0.0;
     for (long long i = threadIdx.x; i < q; i += blockDim.x) {
         const float avg = fmul((float)((long long)gt[i] + 1 + (long long)ge[i]), 0.5f);
-        acc[0] += (double)__frcp_rn(avg);
+        const float rr = __frcp_rn(avg);
+        acc[0] += (double)rr;
+        if (recip) recip[i] = rr;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < kv.nk && avg <= (float)kv.k[j]) acc[1 + j] += 1.0;
+            if (j < kv.nk) {
+                const bool hit = avg <= (float)kv.k[j];
+                if (hit) acc[1 + j] += 1.0;
+                if (hits) hits[i * kv.nk + j] = hit;
+            }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -206,47 +217,35 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 using namespace blp;
 
-extern "C" int blp_eval_rank(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
-                             const float *h_rows, const float *t_rows, const float *r_rows, int64_t b,
-                             const int64_t *filt_indptr, const int64_t *filt_idx, int32_t *gt, int32_t *ge,
-                             int32_t *gt_f, int32_t *ge_f, float *true_score, void *stream) {
-    reset_launch_count();
-    int rc = check_model_dim(model, d);
-    if (rc) return rc;
-    if (b < 0 || n_local < 0) { set_error("negative size"); return BLP_EINVAL; }
-    if (b == 0) return BLP_OK;
-    if (!h_rows || !t_rows || !r_rows || !gt || !ge || !true_score || (n_local > 0 && !ent)) {
-        set_error("null pointer argument");
-        return BLP_EINVAL;
-    }
-    if (filt_indptr && (!gt_f || !ge_f || !filt_idx)) { set_error("filters given without gt_f/ge_f/filt_idx"); return BLP_EINVAL; }
-    if (n_local >= (1ll << 31)) { set_error("n_local too large for int32 counters"); return BLP_EINVAL; }
-    cudaStream_t st = (cudaStream_t)stream;
-
+// Shared body of blp_eval_rank / blp_rank_sweep: true scores (+ counter reset), the sweep, the filter correction.
+static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d, const RowRef &h,
+                     const RowRef &t, const RowRef &r, int64_t b, int64_t tail_off, const int64_t *filt_indptr,
+                     const int64_t *filt_idx, int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
+                     cudaStream_t st) {
     {
         const size_t ts_smem = (size_t)kTrueWarps * 3 * d * sizeof(float);
         const int staged = ts_smem <= 48 * 1024;
         true_score_kernel<<<(unsigned)((b + kTrueWarps - 1) / kTrueWarps), kTrueWarps * 32, staged ? ts_smem : 0, st>>>(
-            model, h_rows, t_rows, r_rows, b, d, staged, true_score, gt, ge);
+            model, h, t, r, b, tail_off, d, staged, true_score, gt, ge);
     }
     count_launch();
     BLP_CUDA(cudaGetLastError());
 
     if (n_local > 0) {
-        if (d == kD && aligned16(ent) && aligned16(h_rows) && aligned16(t_rows) && aligned16(r_rows)) {
+        if (d == kD && aligned16(ent)) {
             SweepArgs a{};
-            a.ent = ent; a.n_local = n_local; a.h_rows = h_rows; a.t_rows = t_rows; a.r_rows = r_rows; a.b = b;
+            a.ent = ent; a.n_local = n_local; a.h = h; a.t = t; a.r = r; a.b = b; a.tail_off = tail_off;
             a.true_score = true_score; a.gt = gt; a.ge = ge; a.scores_out = nullptr; a.ld_scores = 0;
             a.roles = 3; a.groups = 0; a.use_tma = sweep_env_use_tma(); a.negzero2 = kNegZero2;
-            rc = launch_sweep_dyn(model, a, st);
+            const int rc = launch_sweep_dyn(model, a, st);
             if (rc) return rc;
         } else {
             const int threads = 256;
             long long bx = (n_local + threads - 1) / threads;
             if (bx > 1024) bx = 1024;
-            if (2 * b > 65535) { set_error("generic-width sweep: b too large, split the sweep"); return BLP_EINVAL; }
-            dim3 grid((unsigned)bx, (unsigned)(2 * b));
-            sweep_generic_kernel<<<grid, threads, 0, st>>>(model, ent, n_local, d, h_rows, t_rows, r_rows, b, true_score, gt, ge);
+            const long long by = 2 * b < 65535 ? 2 * b : 65535;
+            dim3 grid((unsigned)bx, (unsigned)by);
+            sweep_generic_kernel<<<grid, threads, 0, st>>>(model, ent, n_local, d, h, t, r, b, tail_off, true_score, gt, ge);
             count_launch();
             BLP_CUDA(cudaGetLastError());
         }
@@ -255,13 +254,60 @@ extern "C" int blp_eval_rank(int model, const float *ent, int64_t n_local, int64
         const long long warps = 2 * b;
         const int threads = 128;
         const long long blocks = (warps * 32 + threads - 1) / threads;
-        filter_correct_kernel<<<(unsigned)blocks, threads, 0, st>>>(model, ent, n_local, ent_offset, d, h_rows, t_rows,
-                                                                    r_rows, b, (const long long *)filt_indptr,
+        filter_correct_kernel<<<(unsigned)blocks, threads, 0, st>>>(model, ent, n_local, ent_offset, d, h, t, r, b, tail_off,
+                                                                    (const long long *)filt_indptr,
                                                                     (const long long *)filt_idx, true_score, gt, ge, gt_f, ge_f);
         count_launch();
         BLP_CUDA(cudaGetLastError());
     }
     return BLP_OK;
+}
+
+static int check_rank_args(int model, int d, int64_t b, int64_t n_local, const void *ent, const int64_t *filt_indptr,
+                           const int64_t *filt_idx, const void *gt, const void *ge, const void *gt_f, const void *ge_f,
+                           const void *true_score) {
+    int rc = check_model_dim(model, d);
+    if (rc) return rc;
+    if (b < 0 || n_local < 0) { set_error("negative size"); return BLP_EINVAL; }
+    if (b > 0 && (!gt || !ge || !true_score || (n_local > 0 && !ent))) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if (filt_indptr && (!gt_f || !ge_f || !filt_idx)) { set_error("filters given without gt_f/ge_f/filt_idx"); return BLP_EINVAL; }
+    if (n_local >= (1ll << 31)) { set_error("n_local too large for int32 counters"); return BLP_EINVAL; }
+    return BLP_OK;
+}
+
+extern "C" int blp_eval_rank(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                             const float *h_rows, const float *t_rows, const float *r_rows, int64_t b,
+                             const int64_t *filt_indptr, const int64_t *filt_idx, int32_t *gt, int32_t *ge,
+                             int32_t *gt_f, int32_t *ge_f, float *true_score, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, b, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
+    if (rc) return rc;
+    if (b == 0) return BLP_OK;
+    if (!h_rows || !t_rows || !r_rows) { set_error("null pointer argument"); return BLP_EINVAL; }
+    return rank_impl(model, ent, n_local, ent_offset, d, dense_rows(h_rows), dense_rows(t_rows), dense_rows(r_rows), b, b,
+                     filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score, (cudaStream_t)stream);
+}
+
+extern "C" int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                              const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                              const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                              const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                              int32_t *ge_f, float *true_score, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
+    if (rc) return rc;
+    if (t == 0) return BLP_OK;
+    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
+    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
+    const long long *tr = (const long long *)triples;
+    // train.py:141-143: head_embs = ent_emb[heads], tail_embs = ent_emb[tails], rel_embs = rel_emb(rels)
+    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
+    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
+    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
+    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
+    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
+                     true_score, (cudaStream_t)stream);
 }
 
 extern "C" int blp_score_bcast(int model, const float *heads, int64_t hsA, int64_t hsC, const float *tails,
@@ -282,9 +328,8 @@ extern "C" int blp_score_bcast(int model, const float *heads, int64_t hsA, int64
         SweepArgs a{};
         a.ent = cand_h ? heads : tails; a.n_local = C;
         // the unused query operand aliases a valid row block so the TMA staging reads defined memory
-        a.h_rows = cand_h ? tails : heads; a.t_rows = cand_h ? tails : heads; a.r_rows = rels;
-        if (cand_h) a.t_rows = tails; else a.h_rows = heads;
-        a.b = A; a.true_score = nullptr; a.gt = nullptr; a.ge = nullptr; a.scores_out = out; a.ld_scores = C;
+        a.h = dense_rows(cand_h ? tails : heads); a.t = dense_rows(cand_h ? tails : heads); a.r = dense_rows(rels);
+        a.b = A; a.tail_off = A; a.true_score = nullptr; a.gt = nullptr; a.ge = nullptr; a.scores_out = out; a.ld_scores = C;
         a.roles = cand_h ? 1 : 2; a.groups = 0; a.use_tma = sweep_env_use_tma(); a.negzero2 = kNegZero2;
         return launch_sweep_dyn(model, a, st);
     }
@@ -327,13 +372,18 @@ extern "C" int blp_metrics_from_counts(const int32_t *gt, const int32_t *ge, int
 
 extern "C" int blp_metrics_reduce(const int32_t *gt, const int32_t *ge, int64_t q, const int64_t *k_values_host, int nk,
                                   double *sums, void *stream) {
+    return blp_rank_metrics(gt, ge, q, k_values_host, nk, nullptr, nullptr, sums, stream);
+}
+
+extern "C" int blp_rank_metrics(const int32_t *gt, const int32_t *ge, int64_t q, const int64_t *k_values_host, int nk,
+                                float *recip, uint8_t *hits, double *sums, void *stream) {
     reset_launch_count();
     if (q < 0 || nk < 0 || nk > 8) { set_error("bad q or nk (nk <= 8)"); return BLP_EINVAL; }
     if (!sums || (q > 0 && (!gt || !ge)) || (nk > 0 && !k_values_host)) { set_error("null pointer argument"); return BLP_EINVAL; }
     KValues kv{};
     kv.nk = nk;
     for (int i = 0; i < nk; ++i) kv.k[i] = k_values_host[i];
-    metrics_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt, ge, q, kv, sums);
+    metrics_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt, ge, q, kv, recip, hits, sums);
     count_launch();
     BLP_CUDA(cudaGetLastError());
     return BLP_OK;

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
     const int slot = warp / C::RS, rowgrp = warp % C::RS;
     const float *qv = &sm.qv[slot * C::TQP][0][0][0];
     const int row_off = rowgrp * C::TC * 32 + lane;                        // this lane's first row inside a tile
-    const long long tail_base = (ROLES == 3) ? args.b : 0;                 // tail queries follow the b head queries
+    const long long tail_base = (ROLES == 3) ? args.tail_off : 0;          // output slot of tail query i is tail_off + i
 
     int it = 0;
     long long id = id_begin;
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             const long long tr = t0 + QM::triple(s_, qi);
             float *qp = &sm.qv[ql >> 1][0][0][ql & 1];
             if (tr < args.b) {
-                const float *h = args.h_rows + tr * kD, *t = args.t_rows + tr * kD, *r = args.r_rows + tr * kD;
+                const float *h = args.h.row(tr, kD), *t = args.t.row(tr, kD), *r = args.r.row(tr, kD);
                 if (hp) fold_query<MODEL, true>(h, t, r, j, qp);
                 else fold_query<MODEL, false>(h, t, r, j, qp);
             } else {

@@ -6,15 +6,35 @@ namespace blp {
 
 constexpr int kD = 128;          // specialised row width
 
+// Row i of a query operand: either the i-th row of a dense [b, d] block (idx == NULL) or a gather
+// base[idx[i * idx_stride] - offset] (train.py:141-143 folded into the kernels).  Out-of-range indices are
+// clamped (the true-score kernel flags them with a NaN score).
+struct RowRef {
+    const float *base;
+    const long long *idx;
+    long long idx_stride, offset, limit;
+    __host__ __device__ __forceinline__ bool in_range(long long i) const {
+        if (!idx) return true;
+        const long long r = idx[i * idx_stride] - offset;
+        return r >= 0 && r < limit;
+    }
+    __host__ __device__ __forceinline__ const float *row(long long i, int d) const {
+        if (!idx) return base + i * d;
+        long long r = idx[i * idx_stride] - offset;
+        r = r < 0 ? 0 : (r >= limit ? limit - 1 : r);
+        return base + r * d;
+    }
+};
+inline RowRef dense_rows(const float *p) { return RowRef{p, nullptr, 0, 0, 0}; }
+
 struct SweepArgs {
     const float *ent;        // [n_local, 128]
     long long n_local;
-    const float *h_rows;     // [b, 128]
-    const float *t_rows;
-    const float *r_rows;
+    RowRef h, t, r;          // true head / true tail / relation row of triple i
     long long b;
-    const float *true_score; // [2b] (head queries then tail queries) or NULL when writing scores
-    int *gt;                 // [2b]
+    long long tail_off;      // outputs: head query i -> [i], tail query i -> [tail_off + i]
+    const float *true_score; // indexed like the outputs, or NULL when writing scores
+    int *gt;
     int *ge;
     float *scores_out;       // optional (n_queries, ld_scores) matrix instead of counting
     long long ld_scores;

@@ -420,8 +420,13 @@ extern "C" int blp_train_loss(int model, int loss, const float *ent_embs, const 
     cudaStream_t st = (cudaStream_t)stream;
     const bool grad = grad_ent != nullptr;
     if (grad) {
-        BLP_CUDA(cudaMemsetAsync(grad_ent, 0, sizeof(float) * (size_t)(2 * b) * d, st));
-        BLP_CUDA(cudaMemsetAsync(grad_rel_weight, 0, sizeof(float) * (size_t)num_rel * d, st));
+        const size_t n_ent = (size_t)(2 * b) * d, n_rel = (size_t)num_rel * d;
+        if (grad_rel_weight == grad_ent + n_ent) {   // one allocation (the Python wrapper's layout): one memset
+            BLP_CUDA(cudaMemsetAsync(grad_ent, 0, sizeof(float) * (n_ent + n_rel), st));
+        } else {
+            BLP_CUDA(cudaMemsetAsync(grad_ent, 0, sizeof(float) * n_ent, st));
+            BLP_CUDA(cudaMemsetAsync(grad_rel_weight, 0, sizeof(float) * n_rel, st));
+        }
     }
     TrainArgs a{};
     a.ent = ent_embs; a.rel_weight = rel_weight; a.rels = (const long long *)rels; a.neg_idx = (const long long *)neg_idx;

@@ -80,42 +80,62 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     recip / hits (and recip_f / hits_f) per query, `sums` float64 [sum 1/rank, hits@k...] (and sums_f),
     mrr / hits_at_k (and mrr_f / hits_at_k_f) python floats normalised by 2T (train.py:196-200).
     """
-    count = count_fn or ops.eval_rank
     dev = ent_emb.device
     triples = triples.to(dev).reshape(-1, 3)
     T = triples.shape[0]
-    heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
     world, _ = _world(group)
     filtered = filter_index is not None or filter_csr is not None
-
-    if h_rows is None:
-        h_rows = gather_rows(ent_emb, ent_offset, heads, group)
-    if t_rows is None:
-        t_rows = gather_rows(ent_emb, ent_offset, tails, group)
-    r_rows = rel_weight.detach().index_select(0, rels)                      # train.py:143 rel_emb lookup
-
     names = ("gt", "ge", "gt_f", "ge_f") if filtered else ("gt", "ge")
-    counters = torch.zeros((len(names), 2, T), dtype=torch.int32, device=dev)
-    true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
+
+    def chunk_csr(lo, hi):
+        if not filtered:
+            return None, None
+        if filter_csr is not None:
+            indptr, idx = _slice_csr(filter_csr, lo, hi, T)
+        else:
+            indptr, idx = filter_index.csr(filter_triples[lo:hi])
+        indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev, non_blocking=True)
+        idx = torch.as_tensor(idx if len(idx) else np.zeros(1, np.int64), dtype=torch.int64).to(dev, non_blocking=True)
+        return indptr, idx
+
     launches = 0
-    for lo in range(0, T, chunk):
-        hi = min(T, lo + chunk)
-        indptr = idx = None
-        if filtered:
-            if filter_csr is not None:
-                indptr, idx = _slice_csr(filter_csr, lo, hi, T)
-            else:
-                indptr, idx = filter_index.csr(filter_triples[lo:hi])
-            indptr = torch.as_tensor(indptr, dtype=torch.int64).to(dev, non_blocking=True)
-            idx = torch.as_tensor(idx if len(idx) else np.zeros(1, np.int64), dtype=torch.int64).to(dev, non_blocking=True)
-        res = count(rel_model, ent_emb, h_rows[lo:hi], t_rows[lo:hi], r_rows[lo:hi], indptr, idx, ent_offset)
-        b = hi - lo
-        for i, name in enumerate(names):
-            counters[i, 0, lo:hi] = res[name][:b]
-            counters[i, 1, lo:hi] = res[name][b:]
-        true_score[0, lo:hi] = res["true_score"][:b]
-        true_score[1, lo:hi] = res["true_score"][b:]
-        launches += res.get("launches", 0)
+    if count_fn is None:
+        # native path: the train.py:141-143 gathers run inside the kernels, results land in (2, T) arrays
+        triples = triples.to(torch.int64).contiguous()
+        if world > 1 and h_rows is None:
+            h_rows = gather_rows(ent_emb, ent_offset, triples[:, 0], group)
+            t_rows = gather_rows(ent_emb, ent_offset, triples[:, 1], group)
+        counters = torch.empty((len(names), 2, T), dtype=torch.int32, device=dev)
+        true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
+        outs = {name: counters[i] for i, name in enumerate(names)}
+        outs["true_score"] = true_score
+        for lo in range(0, T, chunk):
+            hi = min(T, lo + chunk)
+            indptr, idx = chunk_csr(lo, hi)
+            launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
+                                             None if h_rows is None else h_rows[lo:hi],
+                                             None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset)
+    else:
+        # test seam: the sharding / collective logic with a CPU stand-in for blp_eval_rank
+        heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
+        if h_rows is None:
+            h_rows = gather_rows(ent_emb, ent_offset, heads, group)
+        if t_rows is None:
+            t_rows = gather_rows(ent_emb, ent_offset, tails, group)
+        r_rows = rel_weight.detach().index_select(0, rels)                  # train.py:143 rel_emb lookup
+        counters = torch.zeros((len(names), 2, T), dtype=torch.int32, device=dev)
+        true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
+        for lo in range(0, T, chunk):
+            hi = min(T, lo + chunk)
+            indptr, idx = chunk_csr(lo, hi)
+            res = count_fn(rel_model, ent_emb, h_rows[lo:hi], t_rows[lo:hi], r_rows[lo:hi], indptr, idx, ent_offset)
+            b = hi - lo
+            for i, name in enumerate(names):
+                counters[i, 0, lo:hi] = res[name][:b]
+                counters[i, 1, lo:hi] = res[name][b:]
+            true_score[0, lo:hi] = res["true_score"][:b]
+            true_score[1, lo:hi] = res["true_score"][b:]
+            launches += res.get("launches", 0)
 
     if world > 1:
         _dist().all_reduce(counters, group=group)                           # the one collective of the sweep
@@ -125,11 +145,9 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     out["launches"] = launches
     if count_fn is None:
         for suffix in ("", "_f") if filtered else ("",):
-            gt, ge = out["gt" + suffix].reshape(-1), out["ge" + suffix].reshape(-1)
-            recip, hits = ops.metrics_from_counts(gt, ge, k_values)
-            sums = ops.metrics_reduce(gt, ge, k_values)
+            recip, hits, sums = ops.rank_metrics(out["gt" + suffix], out["ge" + suffix], k_values)
             out["recip" + suffix], out["hits" + suffix], out["sums" + suffix] = recip, hits, sums
-            out["launches"] += 2
+            out["launches"] += 1
     return out
 
 

@@ -93,15 +93,16 @@ class _FusedLoss(torch.autograd.Function):
         need = ent_embs.requires_grad or rel_weight.requires_grad
         res = ops.train_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=regularizer, want_grad=need)
         if need:
-            ctx.save_for_backward(res["grad_ent"], res["grad_rel_weight"])
-            ctx.ent_shape = ent_embs.shape
+            ctx.save_for_backward(res["grad_all"])
+            ctx.ent_shape, ctx.rel_shape = ent_embs.shape, rel_weight.shape
         return res["loss"].reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        g_ent, g_rel = ctx.saved_tensors
-        g = grad_out.reshape(1).to(torch.float32)
-        return None, None, None, ops.scaled(g_ent, g).reshape(ctx.ent_shape), ops.scaled(g_rel, g), None, None
+        (g_all,) = ctx.saved_tensors
+        g = ops.scaled(g_all, grad_out.reshape(1).to(torch.float32))        # one launch for both gradients
+        n_ent = ctx.ent_shape.numel()
+        return None, None, None, g[:n_ent].view(ctx.ent_shape), g[n_ent:].view(ctx.rel_shape), None, None
 
 
 def fused_compute_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=0.0):

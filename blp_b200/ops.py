@@ -212,6 +212,78 @@ def eval_rank(model, ent, h_rows, t_rows, r_rows, filt_indptr=None, filt_idx=Non
     return out
 
 
+def _kvalues(k_values):
+    ks = [int(v) for v in (k_values.reshape(-1).tolist() if torch.is_tensor(k_values) else k_values)]
+    return ks, (ctypes.c_int64 * max(1, len(ks)))(*ks)
+
+
+def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, t_rows=None, filt_indptr=None,
+                     filt_idx=None, ent_offset=0):
+    """blp_rank_sweep on triples[lo:hi], written straight into the (2, T) arrays of `out`.
+
+    triples (T, 3) int64 contiguous on the device: (head row, tail row, relation id); `out` holds
+    contiguous (2, T) tensors gt, ge, true_score (and gt_f, ge_f when filters are given); row 0 = head
+    predictions, row 1 = tail predictions.  The train.py:141-143 gathers run inside the kernels.
+    """
+    mid = model_id(model)
+    dev = _require_cuda(ent, rel_weight, triples, h_rows, t_rows, filt_indptr, filt_idx)
+    if ent.dtype != torch.float32 or not ent.is_contiguous() or ent.dim() != 2:
+        raise ValueError("ent must be a contiguous fp32 (N, D) tensor")
+    rel_weight = _f32c(rel_weight)
+    n, d = ent.shape
+    T = triples.shape[0]
+    if triples.dtype != torch.int64 or not triples.is_contiguous() or triples.shape != (T, 3):
+        raise ValueError("triples must be a contiguous int64 (T, 3) tensor")
+    b = hi - lo
+    if not (0 <= lo <= hi <= T):
+        raise ValueError("bad chunk bounds")
+    if (h_rows is None) != (t_rows is None):
+        raise ValueError("h_rows and t_rows must both be given or both None")
+    if h_rows is not None:
+        h_rows, t_rows = _f32c(h_rows), _f32c(t_rows)
+        if h_rows.shape != (b, d) or t_rows.shape != (b, d):
+            raise ValueError(f"h_rows / t_rows must be ({b}, {d})")
+
+    def at(name, esize=4):
+        t = out.get(name)
+        if t is None:
+            return None
+        if t.shape != (2, T) or not t.is_contiguous():
+            raise ValueError(f"out[{name!r}] must be a contiguous (2, {T}) tensor")
+        return ctypes.c_void_p(t.data_ptr() + lo * esize)
+
+    if filt_indptr is not None and filt_indptr.numel() != 2 * b + 1:
+        raise ValueError("filt_indptr must have 2B+1 entries")
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        if b > 0:
+            check(lib().blp_rank_sweep(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
+                                       ctypes.c_void_p(triples.data_ptr() + lo * 24), b, _ptr(h_rows), _ptr(t_rows),
+                                       _ptr(filt_indptr), _ptr(filt_idx), T, at("gt"), at("ge"),
+                                       at("gt_f") if filt_indptr is not None else None,
+                                       at("ge_f") if filt_indptr is not None else None, at("true_score"), stream),
+                  "blp_rank_sweep")
+    return _lib.last_launch_count() if b > 0 else 0
+
+
+def rank_metrics(gt, ge, k_values, per_query=True):
+    """utils.py:106-109 + train.py:154-157 in one launch -> (recip (Q,1) f32, hits (Q,k) bool, sums f64 [1+k])."""
+    dev = _require_cuda(gt, ge)
+    ks, karr = _kvalues(k_values)
+    gt, ge = gt.reshape(-1), ge.reshape(-1)
+    if gt.dtype != torch.int32 or ge.dtype != torch.int32 or not gt.is_contiguous() or not ge.is_contiguous():
+        raise ValueError("rank counters must be contiguous int32")
+    q = gt.numel()
+    recip = torch.empty((q, 1), dtype=torch.float32, device=dev) if per_query else None
+    hits = torch.empty((q, len(ks)), dtype=torch.uint8, device=dev) if per_query else None
+    sums = torch.empty(1 + len(ks), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_rank_metrics(_ptr(gt), _ptr(ge), q, karr, len(ks), _ptr(recip), _ptr(hits), _ptr(sums), stream),
+              "blp_rank_metrics")
+    return recip, (hits.view(torch.bool) if hits is not None else None), sums
+
+
 # ------------------------------------------------------ fused compute_loss ----
 _ws_lock = threading.Lock()
 _workspaces = {}
@@ -247,8 +319,12 @@ def train_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=0.0
     loss_out = torch.empty(1, dtype=torch.float32, device=dev)
     pos = torch.empty(b, dtype=torch.float32, device=dev)
     neg = torch.empty((b, k), dtype=torch.float32, device=dev) if want_neg_scores else None
-    g_ent = torch.empty((b, 2, d), dtype=torch.float32, device=dev) if want_grad else None
-    g_rel = torch.empty_like(rel_weight) if want_grad else None
+    g_all = g_ent = g_rel = None
+    if want_grad:
+        # one allocation for both gradients: one memset in the library, one blp_scale in backward
+        g_all = torch.empty(2 * b * d + rel_weight.numel(), dtype=torch.float32, device=dev)
+        g_ent = g_all[:2 * b * d].view(b, 2, d)
+        g_rel = g_all[2 * b * d:].view_as(rel_weight)
     with torch.cuda.device(dev):
         idx, stream = _enter(dev)
         ws = _workspace(idx, stream.value, int(lib().blp_train_workspace_bytes(b, k)))
@@ -256,7 +332,7 @@ def train_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=0.0
                                    _ptr(neg_idx), s0, s1, s2, b, k, d, float(regularizer), _ptr(loss_out), _ptr(pos),
                                    _ptr(neg), _ptr(g_ent), _ptr(g_rel), _ptr(ws), stream), "blp_train_loss")
     return {"loss": loss_out, "pos_scores": pos, "neg_scores": neg, "grad_ent": g_ent, "grad_rel_weight": g_rel,
-            "launches": _lib.last_launch_count(), "workspace": ws}
+            "grad_all": g_all, "launches": _lib.last_launch_count(), "workspace": ws}
 
 
 def scaled(x, scale_dev):

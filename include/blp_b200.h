@@ -103,6 +103,30 @@ int blp_eval_rank(int model, const float *ent, int64_t n_local, int64_t ent_offs
                   int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f,
                   float *true_score, void *stream);
 
+/* ---- a10 + a11 + a12 for a whole sweep, query rows gathered in-kernel ------
+ * Same computation as blp_eval_rank, but the per-batch gathers of train.py:141-143
+ * (ent_emb[heads], ent_emb[tails], rel_emb(rels)) are folded into the kernels:
+ *   triples    [t, 3] int64 (head row, tail row, relation id): GLOBAL table rows, i.e.
+ *              after ent2idx (train.py:132-135); an id outside the table / relation range
+ *              gives that triple a NaN true_score and zero counts
+ *   rel_weight [num_rel, d]
+ *   h_rows, t_rows  optional pre-gathered [t, d] true rows (entity-sharded sweeps, where a
+ *              true row may live on another rank); NULL = gather from `ent`
+ *   tail_off   output slot of tail query i is tail_off + i (head query i -> slot i), so a
+ *              chunk of a longer sweep writes straight into (2, T) arrays: tail_off >= t
+ *   filt_indptr [2t+1]: heads' rows first, then tails' rows (chunk-local), as blp_eval_rank
+ * Launches: true scores, sweep, (filter correction). */
+int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                   const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                   const float *h_rows, const float *t_rows,
+                   const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
+                   int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score, void *stream);
+
+/* utils.py:106-109 + train.py:154-157 in one launch: per-query reciprocal ranks / hits
+ * (either may be NULL) and the fp64 accumulators of blp_metrics_reduce. */
+int blp_rank_metrics(const int32_t *gt, const int32_t *ge, int64_t q, const int64_t *k_values_host, int nk,
+                     float *recip, uint8_t *hits, double *sums, void *stream);
+
 /* ---- a5-a8  LinkPrediction.compute_loss, forward + backward ---------------
  * Replaces models.py:51-70 and its autograd graph with one fused pass.
  *   ent_embs   [b, 2, d]     (models.py:56 chunk -> heads, tails)

@@ -203,3 +203,61 @@ def test_full_size_properties_fb15k237(cuda_device):
     qsel = torch.cat([sel, sel + b])
     assert np.array_equal(full["gt"].cpu()[qsel].numpy(), co["gt"])
     assert np.array_equal(full["ge"].cpu()[qsel].numpy(), co["ge"])
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d,chunk", [(128, 1000), (128, 17), (64, 23)])
+def test_native_sweep_gathers_in_kernel(model, d, chunk, cuda_device):
+    """blp_rank_sweep (train.py:141-143 gathers folded into the kernels, (2, T) outputs, chunk-local CSR)
+    equals blp_eval_rank on pre-gathered rows and the oracle, for any chunking."""
+    n, T = 700, 50
+    ent, rel, heads, tails, rels = make_inputs(model, n, d, T, seed=31 + d)
+    mask = torch.rand(2 * T, n) < 0.03
+    mask[torch.arange(2 * T), torch.cat([heads, tails])] = False
+    indptr, idx = mask_to_csr(mask.numpy())
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy(), indptr, idx)
+    triples = torch.stack([heads, tails, rels], dim=1).to(cuda_device)
+    out = blp_b200.rank_sweep(model, ent.to(cuda_device), rel.to(cuda_device), triples, filter_csr=(indptr, idx), chunk=chunk)
+    for k in ("gt", "ge", "gt_f", "ge_f"):
+        assert out[k].shape == (2, T)
+        assert np.array_equal(out[k].reshape(-1).cpu().numpy(), co[k]), k
+    assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+    # fused metrics kernel == the two-step form
+    recip, hits = ops.metrics_from_counts(out["gt_f"].reshape(-1), out["ge_f"].reshape(-1), [1, 3, 10])
+    assert torch.equal(recip, out["recip_f"]) and torch.equal(hits, out["hits_f"])
+    sums = ops.metrics_reduce(out["gt"].reshape(-1), out["ge"].reshape(-1), [1, 3, 10])
+    assert torch.equal(sums, out["sums"])
+
+
+def test_native_sweep_out_of_range_ids_are_flagged(cuda_device):
+    """train.py:137-138 asserts mapped ids are >= 0; here such a triple gets a NaN true score and zero counts."""
+    n, T = 300, 6
+    ent, rel, heads, tails, rels = make_inputs("transe", n, 128, T, seed=3)
+    triples = torch.stack([heads, tails, rels], dim=1)
+    triples[2, 0] = -1
+    triples[4, 2] = 99
+    out = blp_b200.rank_sweep("transe", ent.to(cuda_device), rel.to(cuda_device), triples.to(cuda_device))
+    ts = out["true_score"].cpu()
+    bad = torch.isnan(ts[0])
+    assert bad.tolist() == [False, False, True, False, True, False]
+    assert out["ge"].cpu()[:, bad].sum() == 0 and bool((out["ge"].cpu()[:, ~bad] >= 1).all())
+
+
+@pytest.mark.parametrize("model", ("transe", "complex"))
+def test_native_sweep_sharded_with_pregathered_rows(model, cuda_device):
+    """Entity-sharded form: every shard gets the replicated true rows; integer counters add up exactly."""
+    n, T = 3000, 70
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, T, seed=17)
+    e, rw = ent.to(cuda_device), rel.to(cuda_device)
+    triples = torch.stack([heads, tails, rels], dim=1).to(cuda_device)
+    full = blp_b200.rank_sweep(model, e, rw, triples)
+    h_rows, t_rows = e[triples[:, 0]], e[triples[:, 1]]
+    acc_gt, acc_ge = torch.zeros_like(full["gt"]), torch.zeros_like(full["ge"])
+    for rank in range(3):
+        lo, hi = blp_b200.shard_bounds(n, 3, rank)
+        part = blp_b200.rank_sweep(model, e[lo:hi].contiguous(), rw, triples, ent_offset=lo, h_rows=h_rows, t_rows=t_rows)
+        assert torch.equal(part["true_score"], full["true_score"])
+        acc_gt += part["gt"]
+        acc_ge += part["ge"]
+    assert torch.equal(acc_gt, full["gt"]) and torch.equal(acc_ge, full["ge"])

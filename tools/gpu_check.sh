@@ -1,0 +1,24 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench line, ncu launch list, ncu --set full of the sweep kernel.
+# Run as: gpurun --timeout 1500 -- 'bash tools/gpu_check.sh'   (outputs under gpurun_out/)
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.txt
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.txt
+echo "== probe"; timeout 300 python tools/probe_fp32.py 2>&1 | tee gpurun_out/probe_fp32.txt
+echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+echo "== sweeps"
+for spec in "transe 1024 14541 20" "distmult 1024 14541 10" "complex 1024 40943 5" "simple 1024 14541 10" "transe 2 4800000 10" "transe 64 4800000 3"; do
+  timeout 300 python tools/run_sweep.py $spec 2>&1 | tail -1 | tee -a gpurun_out/sweeps.txt
+done
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+echo "== ncu full: sweep transe FB"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -f -o gpurun_out/sweep_transe_fb \
+  python tools/run_sweep.py transe 1024 14541 2 > gpurun_out/ncu_fb.log 2>&1
+echo "== ncu full: sweep transe WD (HBM-bound, eval batch 2)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -f -o gpurun_out/sweep_transe_wd \
+  python tools/run_sweep.py transe 2 4800000 2 > gpurun_out/ncu_wd.log 2>&1
+ls -la gpurun_out

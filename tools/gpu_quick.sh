@@ -1,0 +1,7 @@
+#!/bin/bash
+# Quick GPU pass: parity tests + bench line.  gpurun --timeout 900 -- 'bash tools/gpu_quick.sh'
+set -u
+mkdir -p gpurun_out
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.txt
+echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 "$@" 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+tail -5 gpurun_out/bench.err

@@ -221,7 +221,8 @@ using namespace blp;
 static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d, const RowRef &h,
                      const RowRef &t, const RowRef &r, int64_t b, int64_t tail_off, const int64_t *filt_indptr,
                      const int64_t *filt_idx, int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
-                     cudaStream_t st) {
+                     cudaStream_t st, const long long *triples = nullptr, const void *fast_table_ws = nullptr,
+                     void *fast_query_ws = nullptr, float *fast_scores = nullptr, long long fast_ld = 0) {
     {
         const size_t ts_smem = (size_t)kTrueWarps * 3 * d * sizeof(float);
         const int staged = ts_smem <= 48 * 1024;
@@ -231,7 +232,12 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
     count_launch();
     BLP_CUDA(cudaGetLastError());
 
-    if (n_local > 0) {
+    if (n_local > 0 && fast_table_ws) {
+        // tensor-core mode: scores as a 3xTF32 contraction on tcgen05, same counters (blp_fast.cu)
+        const int rc = launch_fast_sweep(model, n_local, ent_offset, h, t, r, triples, b, tail_off, true_score, gt, ge,
+                                         fast_table_ws, fast_query_ws, fast_scores, fast_ld, st);
+        if (rc) return rc;
+    } else if (n_local > 0) {
         if (d == kD && aligned16(ent)) {
             SweepArgs a{};
             a.ent = ent; a.n_local = n_local; a.h = h; a.t = t; a.r = r; a.b = b; a.tail_off = tail_off;
@@ -308,6 +314,43 @@ extern "C" int blp_rank_sweep(int model, const float *ent, int64_t n_local, int6
     if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
     return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
                      true_score, (cudaStream_t)stream);
+}
+
+extern "C" int64_t blp_fast_table_bytes(int64_t n_local) { return fast_table_ws_bytes(n_local); }
+extern "C" int64_t blp_fast_query_bytes(int64_t t) { return fast_query_ws_bytes(t); }
+
+extern "C" int blp_fast_prepare_table(const float *ent, int64_t n_local, int d, void *table_ws, void *stream) {
+    reset_launch_count();
+    if (d != kD) { set_error("fast mode is specialised for d = %d (got %d)", kD, d); return BLP_EDIM; }
+    if (n_local < 0 || !table_ws || (n_local > 0 && !ent)) { set_error("bad argument"); return BLP_EINVAL; }
+    if (!aligned16(ent) || !aligned16(table_ws)) { set_error("ent / table_ws must be 16-byte aligned"); return BLP_EINVAL; }
+    return fast_prepare_table(ent, n_local, table_ws, (cudaStream_t)stream);
+}
+
+extern "C" int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                   const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                                   const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                                   const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                                   int32_t *ge_f, float *true_score, const void *table_ws, void *query_ws,
+                                   float *scores_out, int64_t ld_scores, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
+    if (rc) return rc;
+    if (d != kD) { set_error("fast mode is specialised for d = %d (got %d)", kD, d); return BLP_EDIM; }
+    if (model == BLP_MODEL_TRANSE) { set_error("fast (tensor-core) mode covers distmult / complex / simple only"); return BLP_EINVAL; }
+    if (t == 0) return BLP_OK;
+    if (!rel_weight || !triples || num_rel <= 0 || !table_ws || !query_ws) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if (!aligned16(table_ws) || !aligned16(query_ws)) { set_error("workspaces must be 16-byte aligned"); return BLP_EINVAL; }
+    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
+    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
+    if (scores_out && ld_scores < n_local) { set_error("ld_scores must be >= n_local"); return BLP_EINVAL; }
+    const long long *tr = (const long long *)triples;
+    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
+    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
+    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
+    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
+    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
+                     true_score, (cudaStream_t)stream, tr, table_ws, query_ws, scores_out, ld_scores);
 }
 
 extern "C" int blp_score_bcast(int model, const float *heads, int64_t hsA, int64_t hsC, const float *tails,

@@ -45,6 +45,14 @@ struct SweepArgs {
 };
 
 int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st);
+
+// tensor-core fast mode (blp_fast.cu)
+long long fast_table_ws_bytes(long long n_local);
+long long fast_query_ws_bytes(long long t);
+int fast_prepare_table(const float *ent, long long n_local, void *table_ws, cudaStream_t st);
+int launch_fast_sweep(int model, long long n_local, long long ent_offset, const RowRef &h, const RowRef &t, const RowRef &r,
+                      const long long *triples, long long b, long long tail_off, const float *true_score, int *gt, int *ge,
+                      const void *table_ws, void *query_ws, float *scores_out, long long ld_scores, cudaStream_t st);
 int sweep_env_use_tma();
 constexpr long long kSweepMaxB = 1ll << 40;
 

@@ -61,7 +61,7 @@ def gather_rows(ent_shard, ent_offset, idx, group=None):
 
 def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, filter_triples=None,
                filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384,
-               h_rows=None, t_rows=None, count_fn=None):
+               h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None):
     """Rank every test triple against all candidate entities (train.py:128-171 for the whole sweep).
 
     rel_model   'transe' | 'distmult' | 'complex' | 'simple'
@@ -73,6 +73,11 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 filtered setting (train.py:159-167); or filter_csr = (indptr [2T+1], idx) precomputed with
                 the head-prediction queries of ALL T triples first
     h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
+    mode        "exact" (default): every score carries the reference's fp32 roundings, ranks are bit-exact;
+                "fast": distmult / complex / simple at D = 128 as a 3xTF32 tensor-core contraction
+                (blp_rank_sweep_fast) -- scores within ~1e-6 * sum|terms|, ranks may differ for candidates
+                inside that band around the true score; `fast_table` = ops.fast_table(ent_emb) to reuse
+                the split table across calls
     count_fn    test seam: replaces ops.eval_rank (same signature) so the sharding / collective logic can
                 be exercised without a GPU
 
@@ -105,6 +110,11 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         if world > 1 and h_rows is None:
             h_rows = gather_rows(ent_emb, ent_offset, triples[:, 0], group)
             t_rows = gather_rows(ent_emb, ent_offset, triples[:, 1], group)
+        if mode not in ("exact", "fast"):
+            raise ValueError(f"unknown mode {mode!r}")
+        if mode == "fast" and fast_table is None:
+            fast_table = ops.fast_table(ent_emb)
+            launches += 1
         counters = torch.empty((len(names), 2, T), dtype=torch.int32, device=dev)
         true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
         outs = {name: counters[i] for i, name in enumerate(names)}
@@ -114,7 +124,8 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             indptr, idx = chunk_csr(lo, hi)
             launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
                                              None if h_rows is None else h_rows[lo:hi],
-                                             None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset)
+                                             None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
+                                             fast_table_ws=fast_table if mode == "fast" else None)
     else:
         # test seam: the sharding / collective logic with a CPU stand-in for blp_eval_rank
         heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()

@@ -217,8 +217,21 @@ def _kvalues(k_values):
     return ks, (ctypes.c_int64 * max(1, len(ks)))(*ks)
 
 
+def fast_table(ent):
+    """Split operand table of the tensor-core mode (blp_fast_prepare_table): build once per entity table."""
+    dev = _require_cuda(ent)
+    if ent.dtype != torch.float32 or not ent.is_contiguous() or ent.dim() != 2:
+        raise ValueError("ent must be a contiguous fp32 (N, D) tensor")
+    n, d = ent.shape
+    ws = torch.empty(int(lib().blp_fast_table_bytes(n)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_fast_prepare_table(_ptr(ent), n, d, _ptr(ws), stream), "blp_fast_prepare_table")
+    return ws
+
+
 def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, t_rows=None, filt_indptr=None,
-                     filt_idx=None, ent_offset=0):
+                     filt_idx=None, ent_offset=0, fast_table_ws=None, scores_out=None):
     """blp_rank_sweep on triples[lo:hi], written straight into the (2, T) arrays of `out`.
 
     triples (T, 3) int64 contiguous on the device: (head row, tail row, relation id); `out` holds
@@ -257,12 +270,21 @@ def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, 
     with torch.cuda.device(dev):
         _, stream = _enter(dev)
         if b > 0:
-            check(lib().blp_rank_sweep(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
-                                       ctypes.c_void_p(triples.data_ptr() + lo * 24), b, _ptr(h_rows), _ptr(t_rows),
-                                       _ptr(filt_indptr), _ptr(filt_idx), T, at("gt"), at("ge"),
-                                       at("gt_f") if filt_indptr is not None else None,
-                                       at("ge_f") if filt_indptr is not None else None, at("true_score"), stream),
-                  "blp_rank_sweep")
+            common = (mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
+                      ctypes.c_void_p(triples.data_ptr() + lo * 24), b, _ptr(h_rows), _ptr(t_rows),
+                      _ptr(filt_indptr), _ptr(filt_idx), T, at("gt"), at("ge"),
+                      at("gt_f") if filt_indptr is not None else None,
+                      at("ge_f") if filt_indptr is not None else None, at("true_score"))
+            if fast_table_ws is None:
+                check(lib().blp_rank_sweep(*common, stream), "blp_rank_sweep")
+            else:
+                # tensor-core mode (distmult / complex / simple, d = 128): tolerance-classified parity
+                qws = torch.empty(int(lib().blp_fast_query_bytes(b)), dtype=torch.uint8, device=dev)
+                if scores_out is not None and (scores_out.dtype != torch.float32 or scores_out.shape != (2 * b, n)
+                                               or not scores_out.is_contiguous()):
+                    raise ValueError(f"scores_out must be a contiguous fp32 ({2 * b}, {n}) tensor")
+                check(lib().blp_rank_sweep_fast(*common, _ptr(fast_table_ws), _ptr(qws), _ptr(scores_out), n, stream),
+                      "blp_rank_sweep_fast")
     return _lib.last_launch_count() if b > 0 else 0
 
 

@@ -122,6 +122,30 @@ int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_off
                    const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
                    int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score, void *stream);
 
+/* ---- tensor-core ("fast") mode of the sweep: distmult / complex / simple, d = 128 ----
+ * The bilinear scores are linear in the candidate row once the query side is folded
+ * (models.py:226-248 with the candidate factored out), so the sweep is a (2t x 128) x (128 x n)
+ * contraction: tcgen05.mma kind::tf32 with a 3xTF32 operand split (hi*hi + lo*hi + hi*lo, fp32
+ * accumulation in TMEM) and the rank-count epilogue reading TMEM.  NOT bit-exact (folding and
+ * the summation order differ from models.py:227): scores agree to ~1e-6 * sum|terms| and ranks
+ * differ only for candidates inside that band around the true score.  The true score itself
+ * is the exact one, and the true entity always counts as a tie (utils.py:104-105).
+ *   table_ws   blp_fast_table_bytes(n_local) bytes, filled by blp_fast_prepare_table (once per
+ *              table); query_ws  blp_fast_query_bytes(t) bytes of scratch
+ *   scores_out optional (2t, ld_scores) matrix receiving the fast scores (row q: head queries
+ *              then tail queries; column: local candidate) -- verification aid, NULL normally
+ * Other arguments as blp_rank_sweep. */
+int64_t blp_fast_table_bytes(int64_t n_local);
+int64_t blp_fast_query_bytes(int64_t t);
+int blp_fast_prepare_table(const float *ent, int64_t n_local, int d, void *table_ws, void *stream);
+int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                        const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                        const float *h_rows, const float *t_rows,
+                        const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
+                        int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
+                        const void *table_ws, void *query_ws, float *scores_out, int64_t ld_scores,
+                        void *stream);
+
 /* utils.py:106-109 + train.py:154-157 in one launch: per-query reciprocal ranks / hits
  * (either may be NULL) and the fp64 accumulators of blp_metrics_reduce. */
 int blp_rank_metrics(const int32_t *gt, const int32_t *ge, int64_t q, const int64_t *k_values_host, int nk,

@@ -180,3 +180,38 @@ def eval_rank_batch(model, ent, heads, tails, rel_rows, k_values=(1, 3, 10), fil
         out["ge_f"] = (pf >= st).sum(1)
         out["recip_f"], out["hits_f"] = get_metrics(pf, true, k_values)
     return out
+
+
+# ---- tolerance reference for the tensor-core ("fast") mode -----------------------------------------
+def folded_queries(model, h_rows, t_rows, r_rows):
+    """Coefficient vectors of the bilinear scores with the candidate factored out, in fp64.
+
+    score(candidate e) = C[q] . e  for head prediction (candidate plays `heads`, train.py:146) and tail
+    prediction (candidate plays `tails`, train.py:147).  Derived term by term from models.py:226-248:
+      distmult  sum (h r) t                                   -> head: r*t            tail: h*r
+      complex   sum rr hr tr + rr hi ti + ri hr ti - ri hi tr -> head: (rr tr + ri ti | rr ti - ri tr)
+                                                                 tail: (rr hr - ri hi | rr hi + ri hr)
+      simple    1/2 sum hh ra tt + th rb ht                   -> head: (ra tt | th rb)/2
+                                                                 tail: (rb ht | hh ra)/2
+    Returns (C_head, C_tail), each (B, D) float64.  Used only to classify the fast mode's tolerance.
+    """
+    h, t, r = (np.asarray(x, dtype=np.float64) for x in (h_rows, t_rows, r_rows))
+    if model == "distmult":
+        return r * t, h * r
+    L = h.shape[-1] // 2
+    h1, h2, t1, t2, r1, r2 = h[:, :L], h[:, L:], t[:, :L], t[:, L:], r[:, :L], r[:, L:]
+    if model == "complex":
+        return (np.concatenate([r1 * t1 + r2 * t2, r1 * t2 - r2 * t1], axis=1),
+                np.concatenate([r1 * h1 - r2 * h2, r1 * h2 + r2 * h1], axis=1))
+    if model == "simple":
+        return (np.concatenate([r1 * t2, t1 * r2], axis=1) * 0.5,
+                np.concatenate([r2 * h2, h1 * r1], axis=1) * 0.5)
+    raise ValueError(f"no contraction form for {model}")
+
+
+def fast_mode_reference(model, ent, h_rows, t_rows, r_rows):
+    """fp64 score matrix (2B, N) of the contraction form and its term mass sum_d |c_d e_d| (the tolerance scale)."""
+    ch, ct = folded_queries(model, h_rows, t_rows, r_rows)
+    c = np.concatenate([ch, ct], axis=0)
+    e = np.asarray(ent, dtype=np.float64)
+    return c @ e.T, np.abs(c) @ np.abs(e).T

@@ -1,0 +1,103 @@
+"""Tensor-core (tcgen05, 3xTF32) mode of the eval sweep vs the oracle: tolerance-classified parity.
+
+The fast mode folds the query side (r*t, h*r, ...) and sums in tensor-core order, so it cannot carry the
+reference's fp32 roundings (models.py:227 association).  Contract (north_star "scores within
+1e-5 relative"): |s_fast - s_ref| <= 1e-5 * sum_d |term_d|, and a rank may differ from the exact one only by
+candidates whose reference score lies within that tolerance of the true score."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, np_oracle
+
+import blp_b200
+from blp_b200 import ops
+from test_gpu_eval import make_inputs
+
+pytestmark = pytest.mark.gpu
+FAST_MODELS = ("distmult", "complex", "simple")
+TOL = 1e-5
+
+
+def _run_fast(model, ent, rel, heads, tails, rels, dev, want_scores=True, ent_offset=0, shard=None):
+    e = ent.to(dev)
+    table = e if shard is None else e[shard[0]:shard[1]].contiguous()
+    T = heads.numel()
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    out = {k: torch.empty((2, T), dtype=torch.int32, device=dev) for k in ("gt", "ge")}
+    out["true_score"] = torch.empty((2, T), dtype=torch.float32, device=dev)
+    scores = torch.full((2 * T, table.shape[0]), float("nan"), device=dev) if want_scores else None
+    kw = {}
+    if shard is not None:
+        kw = {"h_rows": e[triples[:, 0]], "t_rows": e[triples[:, 1]]}
+    ops.rank_sweep_chunk(model, table, rel.to(dev), triples, out, 0, T, ent_offset=ent_offset,
+                         fast_table_ws=ops.fast_table(table), scores_out=scores, **kw)
+    torch.cuda.synchronize()
+    return out, scores
+
+
+@pytest.mark.parametrize("model", FAST_MODELS)
+@pytest.mark.parametrize("n,b", [(128, 64), (700, 37), (1000, 64), (5000, 100), (131, 1)])
+def test_fast_scores_and_ranks_within_tolerance(model, n, b, cuda_device):
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=n + b)
+    out, scores = _run_fast(model, ent, rel, heads, tails, rels, cuda_device)
+    h, t, r = ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy()
+    ref, mass = np_oracle.fast_mode_reference(model, ent.numpy(), h, t, r)
+    got = scores.cpu().numpy().astype(np.float64)
+    assert not np.isnan(got).any()
+    err = np.abs(got - ref)
+    assert (err <= TOL * mass + 1e-30).all(), f"max err/mass = {(err / np.maximum(mass, 1e-30)).max():.3e}"
+    # the exact (bit-for-bit reference) path: true scores are shared, counts may differ only inside the band
+    co = c_oracle.eval_rank(model, ent.numpy(), h, t, r, heads.numpy(), tails.numpy(), want_scores=True)
+    assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+    st = co["true_score"].astype(np.float64)[:, None]
+    band = (np.abs(co["scores"].astype(np.float64) - st) <= 2 * TOL * mass).sum(1)       # includes the true entity
+    for k in ("gt", "ge"):
+        diff = np.abs(out[k].reshape(-1).cpu().numpy().astype(np.int64) - co[k].astype(np.int64))
+        assert (diff <= band).all(), (k, int(diff.max()))
+    assert bool((out["gt"] < out["ge"]).all())           # the true entity always ties itself
+
+
+@pytest.mark.parametrize("model", FAST_MODELS)
+def test_fast_matches_exact_mode_on_almost_all_queries(model, cuda_device):
+    """FB15k-237-sized table: the two modes agree on the rank of nearly every query and on MRR."""
+    n, b = 14541, 512
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=11, n_rel=237)
+    dev = cuda_device
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    exact = blp_b200.rank_sweep(model, ent.to(dev), rel.to(dev), triples)
+    fast = blp_b200.rank_sweep(model, ent.to(dev), rel.to(dev), triples, mode="fast")
+    assert torch.equal(exact["true_score"], fast["true_score"])
+    same = ((exact["gt"] == fast["gt"]) & (exact["ge"] == fast["ge"])).float().mean().item()
+    assert same >= 0.97, same
+    assert int((exact["gt"] - fast["gt"]).abs().max()) <= 3
+    me, mf = blp_b200.finalize(exact), blp_b200.finalize(fast)
+    assert abs(me["mrr"] - mf["mrr"]) <= 1e-6
+    for a, c in zip(me["hits_at_k"], mf["hits_at_k"]):
+        assert abs(a - c) <= 2.0 / (2 * b)
+
+
+@pytest.mark.parametrize("model", ("distmult", "complex"))
+def test_fast_shard_sums_equal_full_table(model, cuda_device):
+    n, b = 3000, 50
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=23)
+    full, _ = _run_fast(model, ent, rel, heads, tails, rels, cuda_device, want_scores=False)
+    acc = {k: torch.zeros_like(full[k]) for k in ("gt", "ge")}
+    for rank in range(3):
+        lo, hi = blp_b200.shard_bounds(n, 3, rank)
+        part, _ = _run_fast(model, ent, rel, heads, tails, rels, cuda_device, want_scores=False, ent_offset=lo, shard=(lo, hi))
+        for k in acc:
+            acc[k] += part[k]
+    for k in acc:
+        assert torch.equal(acc[k], full[k]), k
+
+
+def test_fast_mode_rejects_transe_and_other_widths(cuda_device):
+    ent, rel, heads, tails, rels = make_inputs("transe", 300, 128, 4, seed=1)
+    dev = cuda_device
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    with pytest.raises(ValueError):
+        blp_b200.rank_sweep("transe", ent.to(dev), rel.to(dev), triples, mode="fast")
+    ent64 = torch.randn(300, 64)
+    with pytest.raises(ValueError):
+        ops.fast_table(ent64.to(dev))

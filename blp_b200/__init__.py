@@ -14,11 +14,12 @@ All computation runs in libblp_b200.so (blp_b200/csrc, C ABI in include/blp_b200
 """
 from . import _lib, ops  # noqa: F401
 from ._lib import BlpError  # noqa: F401
-from .evaluate import finalize, gather_rows, rank_sweep, shard_bounds  # noqa: F401
+from .evaluate import breakdowns, finalize, gather_rows, rank_sweep, shard_bounds  # noqa: F401
 from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPrediction,  # noqa: F401
                      complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,
                      margin_loss, nll_loss, simple_score, transe_score)
-from .utils import TripleFilterIndex, get_metrics, make_ent2idx  # noqa: F401
+from .utils import (DeviceFilterIndex, TripleFilterIndex, get_metrics, get_negative_sampling_indices,  # noqa: F401
+                    make_ent2idx)  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -40,6 +40,12 @@ SYMBOLS = {
     "blp_scale": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "blp_pair_loss": (_i32, [_i32, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "blp_l2_regularization": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "blp_filter_index_bytes": (_i64, [_i64]),
+    "blp_filter_index_build": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "blp_filter_correct": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64,
+                                  _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_mrr_breakdown": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "blp_negative_sample": (_i32, [_i64, _i64, _i64, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "blp_profile_events": (_i32, [_i32, _vp, _vp]),
     "blp_pipe_probe": (_i32, [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }

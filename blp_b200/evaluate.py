@@ -69,9 +69,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 not distributed); row j is candidate `ent_offset + j`
     rel_weight  (R, D) relation table (model.rel_emb.weight)
     triples     (T, 3) int64 (head_row, tail_row, rel_id): table ROWS, i.e. after ent2idx (train.py:132-135)
-    filter_index / filter_triples   a utils.TripleFilterIndex and the (T, 3) entity-ID triples for the
-                filtered setting (train.py:159-167); or filter_csr = (indptr [2T+1], idx) precomputed with
-                the head-prediction queries of ALL T triples first
+    filter_index / filter_triples   the filtered setting (train.py:159-167): a utils.DeviceFilterIndex (built once
+                per evaluation, lookups run on the device, `filter_triples` not needed), or a host-side
+                utils.TripleFilterIndex plus the (T, 3) entity-ID triples; or filter_csr = (indptr [2T+1], idx)
+                precomputed with the head-prediction queries of ALL T triples first
     h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
     mode        "exact" (default): every score carries the reference's fp32 roundings, ranks are bit-exact;
                 "fast": distmult / complex / simple at D = 128 as a 3xTF32 tensor-core contraction
@@ -91,9 +92,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     world, _ = _world(group)
     filtered = filter_index is not None or filter_csr is not None
     names = ("gt", "ge", "gt_f", "ge_f") if filtered else ("gt", "ge")
+    dev_index = filter_index if hasattr(filter_index, "workspace") else None     # utils.DeviceFilterIndex
 
     def chunk_csr(lo, hi):
-        if not filtered:
+        if not filtered or dev_index is not None:
             return None, None
         if filter_csr is not None:
             indptr, idx = _slice_csr(filter_csr, lo, hi, T)
@@ -126,6 +128,12 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                                              None if h_rows is None else h_rows[lo:hi],
                                              None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
                                              fast_table_ws=fast_table if mode == "fast" else None)
+            if dev_index is not None:
+                # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
+                launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
+                                               dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
+                                               None if h_rows is None else h_rows[lo:hi],
+                                               None if t_rows is None else t_rows[lo:hi], ent_offset)
     else:
         # test seam: the sharding / collective logic with a CPU stand-in for blp_eval_rank
         heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
@@ -160,6 +168,32 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             out["recip" + suffix], out["hits" + suffix], out["sums" + suffix] = recip, hits, sums
             out["launches"] += 1
     return out
+
+
+def breakdowns(out, triples_ids, new_entities=None, rel_categories=None, max_ent_id=None):
+    """train.py:173-188 on the device: MRR split by the position of new entities (utils.py:114-147) and by
+    relation category (utils.py:150-168), from the FILTERED reciprocal ranks of a finished sweep.
+
+    triples_ids (T, 3) entity IDS; new_entities: iterable of ids or a bool/uint8 mask; rel_categories (R,) int64.
+    Returns dict(mrr_by_position (3,), mrr_pos_counts (3,), mrr_by_category (2, 4), mrr_cat_count (1, 4)) as
+    float64 device tensors (the reference accumulates the same sums batch by batch in fp32)."""
+    recip = out["recip_f"] if "recip_f" in out else out["recip"]
+    dev = recip.device
+    triples_ids = torch.as_tensor(triples_ids).to(dev)
+    is_new = None
+    if new_entities is not None:
+        if torch.is_tensor(new_entities) and new_entities.dtype in (torch.bool, torch.uint8):
+            is_new = new_entities.to(dev)
+        else:
+            ids = torch.as_tensor(sorted(new_entities), dtype=torch.int64)
+            size = int(max(int(max_ent_id or 0), int(triples_ids[:, :2].max().item()), int(ids.max().item()) if ids.numel() else 0)) + 1
+            is_new = torch.zeros(size, dtype=torch.uint8)
+            is_new[ids] = 1
+            is_new = is_new.to(dev)
+    cats = None if rel_categories is None else torch.as_tensor(rel_categories).to(dev)
+    res = ops.mrr_breakdown(recip, triples_ids, is_new, cats)
+    return {"mrr_by_position": res[0:3], "mrr_pos_counts": res[3:6], "mrr_by_category": res[6:14].view(2, 4),
+            "mrr_cat_count": res[14:18].view(1, 4)}
 
 
 def finalize(out, num_queries=None):

@@ -306,6 +306,96 @@ def rank_metrics(gt, ge, k_values, per_query=True):
     return recip, (hits.view(torch.bool) if hits is not None else None), sums
 
 
+# ------------------------------------------------ device-resident filter index ----
+def filter_index_build(edges, ent2idx, n_rows, num_rel):
+    """utils.get_triple_filters (utils.py:46-83) as a lookup structure built once per evaluation.
+
+    edges (E, 3) int64 CUDA tensor of (head id, tail id, rel); ent2idx 1-D int64 CUDA tensor (id -> row or -1) or
+    None when ids are rows.  Returns the opaque index workspace (uint8 tensor) for `filter_correct`."""
+    dev = _require_cuda(edges, ent2idx)
+    edges = edges.to(torch.int64).reshape(-1, 3).contiguous()
+    e = edges.shape[0]
+    if ent2idx is not None:
+        ent2idx = ent2idx.to(torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        nbytes = int(lib().blp_filter_index_bytes(e))
+        if nbytes < 0:
+            check(-3, "blp_filter_index_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib().blp_filter_index_build(_ptr(edges) if e else None, e, _ptr(ent2idx),
+                                           ent2idx.numel() if ent2idx is not None else 0, int(n_rows), int(num_rel),
+                                           _ptr(ws), nbytes, stream), "blp_filter_index_build")
+    return ws
+
+
+def filter_correct(model, ent, rel_weight, triples, out, lo, hi, index_ws, num_edges, n_rows, h_rows=None, t_rows=None,
+                   ent_offset=0):
+    """Filtered counters of triples[lo:hi] from the raw ones already in `out` (train.py:159-167)."""
+    mid = model_id(model)
+    dev = _require_cuda(ent, rel_weight, triples, index_ws, h_rows, t_rows)
+    rel_weight = _f32c(rel_weight)
+    n, d = ent.shape
+    T = triples.shape[0]
+    b = hi - lo
+    if b <= 0:
+        return 0
+    if h_rows is not None:
+        h_rows, t_rows = _f32c(h_rows), _f32c(t_rows)
+
+    def at(name):
+        t = out[name]
+        if t.shape != (2, T) or not t.is_contiguous():
+            raise ValueError(f"out[{name!r}] must be a contiguous (2, {T}) tensor")
+        return ctypes.c_void_p(t.data_ptr() + lo * 4)
+
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_filter_correct(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
+                                       ctypes.c_void_p(triples.data_ptr() + lo * 24), b, _ptr(h_rows), _ptr(t_rows),
+                                       _ptr(index_ws), int(num_edges), int(n_rows), T, at("true_score"), at("gt"), at("ge"),
+                                       at("gt_f"), at("ge_f"), stream), "blp_filter_correct")
+    return _lib.last_launch_count()
+
+
+def mrr_breakdown(recip, triples_ids, is_new=None, rel_categories=None):
+    """train.py:173-188 (utils.split_by_new_position / split_by_category) -> float64 device tensor [18]:
+    mrr_by_position[3], position counts[3], mrr_by_category[2*4], category counts[4]."""
+    dev = _require_cuda(recip, triples_ids, is_new, rel_categories)
+    recip = _f32c(recip).reshape(-1)
+    triples_ids = triples_ids.to(torch.int64).reshape(-1, 3).contiguous()
+    t = triples_ids.shape[0]
+    if recip.numel() != 2 * t:
+        raise ValueError("recip must hold 2T reciprocal ranks (head queries, then tail queries)")
+    if is_new is not None:
+        is_new = is_new.to(torch.uint8).contiguous()
+    if rel_categories is not None:
+        rel_categories = rel_categories.to(torch.int64).contiguous()
+    out = torch.empty(18, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_mrr_breakdown(_ptr(recip), t, t, _ptr(triples_ids), _ptr(is_new),
+                                      is_new.numel() if is_new is not None else 0, _ptr(rel_categories),
+                                      rel_categories.numel() if rel_categories is not None else 0, _ptr(out), stream),
+              "blp_mrr_breakdown")
+    return out
+
+
+# ------------------------------------------------------- negative sampler ----
+def negative_sample(batch_size, num_negatives, repeats=1, *, device, seed=0, offset=0):
+    """data.get_negative_sampling_indices (data.py:35-81) on the device: int64 (batch*repeats, num_negatives, 2)
+    with the reference's strides (a transposed view of a (K, B*repeats, 2) buffer)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.BlpError("blp_b200 runs on sm_100 CUDA devices only; there is no CPU fallback")
+    storage = torch.empty((int(num_negatives), int(batch_size) * int(repeats), 2), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_negative_sample(int(batch_size), int(num_negatives), int(repeats), int(seed) & (2 ** 64 - 1),
+                                        int(offset) & (2 ** 64 - 1), _ptr(storage), stream), "blp_negative_sample")
+    return storage.transpose(0, 1)
+
+
 # ------------------------------------------------------ fused compute_loss ----
 _ws_lock = threading.Lock()
 _workspaces = {}

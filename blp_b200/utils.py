@@ -96,3 +96,29 @@ class TripleFilterIndex:
         for q in range(2 * b):
             mask[q, idx[indptr[q]:indptr[q + 1]]] = True
         return mask[:b], mask[b:]
+
+
+class DeviceFilterIndex:
+    """The filtering graph as a device-resident lookup structure (blp_filter_index_build), built once per
+    evaluation: replaces the per-batch utils.get_triple_filters call, its dense (B, N) masks and their H2D copy
+    (utils.py:46-83, train.py:160-164).  `rank_sweep(filter_index=DeviceFilterIndex(...))` then derives the
+    filtered ranks with one sparse correction launch per chunk and no host work."""
+
+    def __init__(self, edges, ent2idx, num_rows, num_relations, device):
+        """edges: (E, 3) (head id, tail id, rel) -- e.g. list(graph.edges(keys=True)); ent2idx: id -> row or -1
+        (None when ids are table rows); num_rows: rows of the whole entity table."""
+        dev = torch.device(device)
+        edges = torch.as_tensor(np.asarray(edges.cpu() if torch.is_tensor(edges) else edges, dtype=np.int64).reshape(-1, 3))
+        self.num_edges = int(edges.shape[0])
+        self.num_rows, self.num_relations = int(num_rows), int(num_relations)
+        e2i = None
+        if ent2idx is not None:
+            e2i = torch.as_tensor(np.asarray(ent2idx.cpu() if torch.is_tensor(ent2idx) else ent2idx, dtype=np.int64)).to(dev)
+        self.workspace = ops.filter_index_build(edges.to(dev), e2i, self.num_rows, self.num_relations)
+        self.device = dev
+
+
+def get_negative_sampling_indices(batch_size, num_negatives, repeats=1, *, device, seed=0, offset=0):
+    """data.get_negative_sampling_indices (data.py:35-81) drawn on the device (blp_negative_sample): same shape,
+    dtype and strides as the reference's return value; pass a fresh `offset` (e.g. the step number) per call."""
+    return ops.negative_sample(batch_size, num_negatives, repeats, device=device, seed=seed, offset=offset)

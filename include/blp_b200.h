@@ -199,6 +199,52 @@ int blp_pair_loss(int loss, const float *pos, const float *neg, int64_t neg_row_
 int blp_l2_regularization(const float *heads, int64_t n_heads, const float *tails, int64_t n_tails,
                           const float *rels, int64_t n_rels, float *out, void *stream);
 
+/* ---- a12 / next row f1  filtered ranks from a device-resident filter index -----------------
+ * Replaces utils.get_triple_filters (utils.py:46-83: per-batch dense (B, N) bool masks built with Python
+ * loops over the graph's edges), the mask H2D and the second get_metrics pass (train.py:159-167).
+ * The filtering graph is turned ONCE per evaluation into two sorted arrays of composite keys
+ * ((rel * n_rows + fixed_row) * n_rows + other_row); the known tails of (head, rel) / heads of (tail, rel)
+ * are one run found by binary search.
+ *   edges      [num_edges, 3] int64 (head id, tail id, rel) -- graph.edges(keys=True) of the filtering graph
+ *   ent2idx    [n_ids] int64 entity id -> table row or -1 (utils.py:31-43); NULL = ids are rows already
+ *   n_rows     rows of the WHOLE entity table (all shards); num_rel relation count
+ *   index_ws   blp_filter_index_bytes(num_edges) bytes, 256-byte aligned; holds the index afterwards
+ * Edges touching an entity without a row are dropped (utils.py:72-73,79-80); parallel edges collapse. */
+int64_t blp_filter_index_bytes(int64_t num_edges);
+int blp_filter_index_build(const int64_t *edges, int64_t num_edges, const int64_t *ent2idx, int64_t n_ids,
+                           int64_t n_rows, int64_t num_rel, void *index_ws, int64_t index_bytes, void *stream);
+/* Filtered counters from the raw ones (run after blp_rank_sweep / blp_rank_sweep_fast on the same stream):
+ * gt_f = gt - #{filtered candidates in this shard with s > s_true}, likewise ge_f.  A candidate is filtered
+ * for a head query iff (cand, tail, rel) is an edge and cand != head (utils.py:76-81); for a tail query iff
+ * (head, cand, rel) is an edge and cand != tail (utils.py:69-74).  triples / h_rows / t_rows / tail_off as
+ * blp_rank_sweep; true_score, gt, ge are that call's outputs. */
+int blp_filter_correct(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                       const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                       const float *h_rows, const float *t_rows, const void *index_ws, int64_t num_edges,
+                       int64_t n_rows, int64_t tail_off, const float *true_score, const int32_t *gt,
+                       const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream);
+
+/* ---- next row f2  MRR breakdowns of train.py:173-188 (utils.py:114-168) in one launch ---------
+ *   recip      reciprocal ranks, head query i at [i], tail query i at [tail_off + i]
+ *   triples    [t, 3] int64 (head id, tail id, rel) ENTITY IDS (as the reference's loops see them)
+ *   is_new     [n_ids] bytes, 1 = entity is new (utils.split_by_new_position), or NULL
+ *   rel_categories [num_rel] int64 in [0, 4) (utils.split_by_category), or NULL
+ *   out        18 doubles (overwritten): mrr_by_position[3] (both new / head new / tail new), counts[3],
+ *              mrr_by_category[2][4] (row 0 head prediction, row 1 tail prediction), category counts[4] */
+int blp_mrr_breakdown(const float *recip, int64_t t, int64_t tail_off, const int64_t *triples,
+                      const uint8_t *is_new, int64_t n_ids, const int64_t *rel_categories, int64_t num_rel,
+                      double *out, void *stream);
+
+/* ---- a14 / next row f3  in-batch negative sampling indices (data.py:35-81) --------------------
+ * out is the (num_neg, batch * repeats, 2) int64 buffer whose transposed view (batch * repeats, num_neg, 2),
+ * element strides (2, 2 * batch * repeats, 1), is what get_negative_sampling_indices returns (data.py:77-79)
+ * and what blp_train_loss reads in place.  Every negative keeps one entity of its own pair (2b or 2b + 1)
+ * and replaces the other (fair coin, data.py:71) by a uniform draw from the 2 * batch - 2 entities of the
+ * other pairs (data.py:60-65).  Philox4x32-10 keyed by seed, counter (element, offset): the stream differs
+ * from torch's CPU generator by construction -- distributional parity only. */
+int blp_negative_sample(int64_t batch, int64_t num_neg, int64_t repeats, uint64_t seed, uint64_t offset,
+                        int64_t *out, void *stream);
+
 /* ---- measurement aid ------------------------------------------------------
  * FP32 pipe micro-benchmarks used by bench.py to measure the lane-op rate the
  * ALU-bound exact sweeps are compared against ("measure

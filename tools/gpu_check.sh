@@ -9,7 +9,8 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== probe"; timeout 300 python tools/probe_fp32.py 2>&1 | tee gpurun_out/probe_fp32.txt
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2> gpurun_out/bench.err | tee gpurun_out/bench.json
 echo "== sweeps"
-for spec in "transe 1024 14541 20" "distmult 1024 14541 10" "complex 1024 40943 5" "simple 1024 14541 10" "transe 2 4800000 10" "transe 64 4800000 3"; do
+for spec in "transe 1024 14541 20" "distmult 1024 14541 10" "complex 1024 40943 5" "simple 1024 14541 10" "transe 2 4800000 10" "transe 64 4800000 3" \
+            "distmult 1024 14541 20 fast" "complex 1024 40943 10 fast" "simple 1024 14541 20 fast" "distmult 8192 14541 10 fast" "distmult 64 4800000 3 fast"; do
   timeout 300 python tools/run_sweep.py $spec 2>&1 | tail -1 | tee -a gpurun_out/sweeps.txt
 done
 echo "== ncu launch list"
@@ -21,4 +22,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:swee
 echo "== ncu full: sweep transe WD (HBM-bound, eval batch 2)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -f -o gpurun_out/sweep_transe_wd \
   python tools/run_sweep.py transe 2 4800000 2 > gpurun_out/ncu_wd.log 2>&1
+echo "== ncu full: fast sweep distmult FB (tcgen05)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fast_sweep_kernel -s 3 -c 1 -f -o gpurun_out/sweep_fast_distmult_fb \
+  python tools/run_sweep.py distmult 1024 14541 2 fast > gpurun_out/ncu_fast.log 2>&1
 ls -la gpurun_out

@@ -59,6 +59,8 @@ def parse():
     p.add_argument("--mode", default="exact", choices=("exact", "fast"),
                    help="eval sweep arithmetic: exact = reference fp32 order (bit-exact ranks); fast = tcgen05 3xTF32 "
                         "contraction (distmult / complex / simple only, tolerance-classified)")
+    p.add_argument("--eager-train", action="store_true",
+                   help="run compute_loss forward+backward eagerly instead of replaying blp_b200.GraphedLossStep")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the Wikidata5M-scale HBM-bound / entity-sharded sweep legs")
     p.add_argument("--wd-entities", type=int, default=4_800_000, help="rows of the Wikidata5M-scale table (whole table)")
@@ -219,6 +221,7 @@ def config_dict(args, w, e, flush):
                         f"ranked against all entities (heads and tails) per step",
             "entities": w["n"], "relations": w["r"], "dim": w["d"], "rel_model": args.model, "loss": args.loss,
             "train_batch": w["b"], "negatives": w["k"], "eval_triples_per_step": e, "eval_mode": args.mode,
+            "train_step": "eager autograd" if args.eager_train else "CUDA-graph replay of compute_loss forward+backward (blp_b200.GraphedLossStep)",
             "triples_per_step": step_triples(w, e),
             "l2": ("flushed between timed steps (256 MiB write)" if flush else "not flushed (table is L2-resident by design)"),
             "parallelism": f"replicas x{args.gpus}: train sub-batches independent, eval queries sharded, table replicated"}
@@ -345,11 +348,19 @@ def main_b200(args):
 
     launches = {"n": 0}
 
+    # the launch-bound training step replays a CUDA graph of `loss = model.compute_loss(...); loss.backward()`
+    graphed = None if args.eager_train else blp_b200.GraphedLossStep(model, b, k)
+    if graphed is not None:
+        graphed(ent_embs, rels, neg)                  # resident inputs: loaded into the static buffers once
+
     def train_step():
-        x = ent_embs.detach().requires_grad_(True)
-        rel_w.grad = None
-        loss = model.compute_loss(x, rels, neg)
-        loss.backward()
+        if graphed is not None:
+            loss, _ = graphed.replay()
+        else:
+            x = ent_embs.detach().requires_grad_(True)
+            rel_w.grad = None
+            loss = model.compute_loss(x, rels, neg)
+            loss.backward()
         launches["n"] += 1 + 1            # fused fwd+bwd kernel, one blp_scale in autograd's backward
         return loss
 
@@ -390,19 +401,26 @@ def main_b200(args):
     sampler.start()
     time.sleep(0.12)
     t_wall0 = time.perf_counter()
+    host_s = 0.0
     for i in range(steps):
         if flush:
             flush_buf.fill_(i & 0xFF)
+        h0 = time.perf_counter()
         step_ev[i][0].record()
         lib.blp_profile_events(1, ctypes.c_void_p(prof[i][0].cuda_event), ctypes.c_void_p(prof[i][1].cuda_event))
         step(warmup + i)
         step_ev[i][1].record()
+        host_s += time.perf_counter() - h0
     lib.blp_profile_events(0, None, None)
     barrier()
     t_wall1 = time.perf_counter()
     timed_launches = launches["n"]
     step_ms = [a_.elapsed_time(b_) for a_, b_ in step_ev]
     kern_ms = [a_.elapsed_time(b_) for a_, b_ in prof]
+    if os.environ.get("BLP_BENCH_DEBUG"):
+        sys.stderr.write(f"[rank {rank}] step_ms min/med/max {min(step_ms):.3f}/{statistics.median(step_ms):.3f}/{max(step_ms):.3f} "
+                         f"kern_ms med {statistics.median(kern_ms):.3f} host enqueue {1e3 * host_s / steps:.3f} ms/step "
+                         f"cpus {len(os.sched_getaffinity(0))} dev {torch.cuda.current_device()}\n")
     total_ms = sum(step_ms)
     # keep the GPU under the same load until nvidia-smi has a few samples, if the timed region was short
     if t_wall1 - t_wall0 < 1.0:
@@ -434,13 +452,16 @@ def main_b200(args):
     host_sums = torch.empty(4, dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
-        x = h_ent_embs.to(dev, non_blocking=True).requires_grad_(True)
-        r_ = h_rels.to(dev, non_blocking=True)
-        ng = h_neg.to(dev, non_blocking=True).transpose(0, 1)
         tr = h_triples[i % len(h_triples)].to(dev, non_blocking=True)
-        rel_w.grad = None
-        loss = model.compute_loss(x, r_, ng)
-        loss.backward()
+        if graphed is not None:
+            loss, _ = graphed(h_ent_embs, h_rels, h_neg)          # H2D into the static buffers, then one graph launch
+        else:
+            x = h_ent_embs.to(dev, non_blocking=True).requires_grad_(True)
+            r_ = h_rels.to(dev, non_blocking=True)
+            ng = h_neg.to(dev, non_blocking=True).transpose(0, 1)
+            rel_w.grad = None
+            loss = model.compute_loss(x, r_, ng)
+            loss.backward()
         out = blp_b200.rank_sweep(args.model, ent, rel_w, tr, chunk=e, mode=args.mode, fast_table=fast_ws)
         # D2H: the loss scalar (train.py:352) + the 4 fp64 metric accumulators (train.py:154-157), one sync
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)

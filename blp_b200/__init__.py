@@ -14,6 +14,7 @@ All computation runs in libblp_b200.so (blp_b200/csrc, C ABI in include/blp_b200
 """
 from . import _lib, ops  # noqa: F401
 from ._lib import BlpError  # noqa: F401
+from .graphs import GraphedLossStep  # noqa: F401
 from .evaluate import breakdowns, finalize, gather_rows, rank_sweep, shard_bounds  # noqa: F401
 from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPrediction,  # noqa: F401
                      complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,

@@ -34,9 +34,12 @@ def _dist():
 
 
 def _world(group):
-    dist = _dist()
-    if group is None and not (dist.is_available() and dist.is_initialized()):
+    """(world size, rank) of an entity-sharded sweep.  `group=None` means NOT sharded (this process holds the whole
+    table) even when torch.distributed is initialised -- e.g. data-parallel replicas each ranking their own triples;
+    pass `torch.distributed.group.WORLD` (or a sub-group) to shard the candidate axis over its ranks."""
+    if group is None:
         return 1, 0
+    dist = _dist()
     return dist.get_world_size(group), dist.get_rank(group)
 
 
@@ -73,6 +76,8 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 per evaluation, lookups run on the device, `filter_triples` not needed), or a host-side
                 utils.TripleFilterIndex plus the (T, 3) entity-ID triples; or filter_csr = (indptr [2T+1], idx)
                 precomputed with the head-prediction queries of ALL T triples first
+    ent_offset / group   entity-sharded sweeps: global row id of ent_emb[0] and the process group whose ranks hold the
+                other row blocks (one all-reduce of the counters per sweep); group=None = not sharded
     h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
     mode        "exact" (default): every score carries the reference's fp32 roundings, ranks are bit-exact;
                 "fast": distmult / complex / simple at D = 128 as a 3xTF32 tensor-core contraction
@@ -87,7 +92,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     mrr / hits_at_k (and mrr_f / hits_at_k_f) python floats normalised by 2T (train.py:196-200).
     """
     dev = ent_emb.device
-    triples = triples.to(dev).reshape(-1, 3)
+    if triples.device != dev:
+        triples = triples.to(dev)
+    if triples.dim() != 2:
+        triples = triples.reshape(-1, 3)
     T = triples.shape[0]
     world, _ = _world(group)
     filtered = filter_index is not None or filter_csr is not None
@@ -108,7 +116,8 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     launches = 0
     if count_fn is None:
         # native path: the train.py:141-143 gathers run inside the kernels, results land in (2, T) arrays
-        triples = triples.to(torch.int64).contiguous()
+        if triples.dtype != torch.int64 or not triples.is_contiguous():
+            triples = triples.to(torch.int64).contiguous()
         if world > 1 and h_rows is None:
             h_rows = gather_rows(ent_emb, ent_offset, triples[:, 0], group)
             t_rows = gather_rows(ent_emb, ent_offset, triples[:, 1], group)
@@ -117,8 +126,9 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         if mode == "fast" and fast_table is None:
             fast_table = ops.fast_table(ent_emb)
             launches += 1
-        counters = torch.empty((len(names), 2, T), dtype=torch.int32, device=dev)
-        true_score = torch.empty((2, T), dtype=torch.float32, device=dev)
+        # one allocation: the int32 counters, then the fp32 true scores
+        buf = torch.empty((len(names) + 1, 2, T), dtype=torch.int32, device=dev)
+        counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
         outs = {name: counters[i] for i, name in enumerate(names)}
         outs["true_score"] = true_score
         for lo in range(0, T, chunk):

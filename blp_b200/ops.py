@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns the device memory and the stream; every
 computation is a call into libblp_b200.so.  Nothing in this module computes a
 score, a loss or a rank with torch ops, and nothing falls back to the CPU.
 """
+import contextlib
 import ctypes
 import threading
 
@@ -38,6 +39,15 @@ def _enter(dev):
         check(lib().blp_device_check(idx), "blp_device_check")
         _checked_devices.add(idx)
     return idx, ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _guard(dev):
+    """Device guard that costs nothing when `dev` is already the current device (the common case)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _NULL_CTX if torch.cuda.current_device() == idx else torch.cuda.device(idx)
 
 
 def _ptr(t):
@@ -115,7 +125,7 @@ def score(model, heads, tails, rels):
         sA = _prod(sh[split:]) * d if (a_full and A > 1) else 0
         sC = d if (c_full and C > 1) else 0
         args += [_ptr(x), sA, sC]
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         if A * C > 0:
             check(lib().blp_score_bcast(mid, *args, A, C, d, _ptr(out), stream), "blp_score_bcast")
@@ -135,7 +145,7 @@ def rank_counts(pred_scores, true_idx):
         raise ValueError("true_idx must have one entry per row of pred_scores")
     gt = torch.empty(q, dtype=torch.int32, device=dev)
     ge = torch.empty(q, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_rank_counts(_ptr(pred), q, n, pred.stride(0) if q > 1 else n, _ptr(ti), _ptr(gt), _ptr(ge), stream),
               "blp_rank_counts")
@@ -150,7 +160,7 @@ def metrics_from_counts(gt, ge, k_values):
     recip = torch.empty((q, 1), dtype=torch.float32, device=dev)
     hits = torch.empty((q, len(ks)), dtype=torch.uint8, device=dev)
     karr = (ctypes.c_int64 * max(1, len(ks)))(*ks)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_metrics_from_counts(_ptr(gt.contiguous()), _ptr(ge.contiguous()), q, karr, len(ks),
                                             _ptr(recip), _ptr(hits), stream), "blp_metrics_from_counts")
@@ -166,7 +176,7 @@ def metrics_reduce(gt, ge, k_values):
     gt, ge = gt.reshape(-1).contiguous(), ge.reshape(-1).contiguous()
     if gt.dtype != torch.int32 or ge.dtype != torch.int32:
         raise ValueError("rank counters must be int32")
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_metrics_reduce(_ptr(gt), _ptr(ge), gt.numel(), karr, len(ks), _ptr(sums), stream),
               "blp_metrics_reduce")
@@ -203,7 +213,7 @@ def eval_rank(model, ent, h_rows, t_rows, r_rows, filt_indptr=None, filt_idx=Non
         gtf = torch.empty(2 * b, dtype=torch.int32, device=dev)
         gef = torch.empty(2 * b, dtype=torch.int32, device=dev)
         out["gt_f"], out["ge_f"] = gtf, gef
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_eval_rank(mid, _ptr(ent), n, int(ent_offset), d, _ptr(h_rows), _ptr(t_rows), _ptr(r_rows), b,
                                   _ptr(filt_indptr), _ptr(filt_idx), _ptr(gt), _ptr(ge), _ptr(gtf), _ptr(gef),
@@ -224,7 +234,7 @@ def fast_table(ent):
         raise ValueError("ent must be a contiguous fp32 (N, D) tensor")
     n, d = ent.shape
     ws = torch.empty(int(lib().blp_fast_table_bytes(n)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_fast_prepare_table(_ptr(ent), n, d, _ptr(ws), stream), "blp_fast_prepare_table")
     return ws
@@ -267,7 +277,7 @@ def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, 
 
     if filt_indptr is not None and filt_indptr.numel() != 2 * b + 1:
         raise ValueError("filt_indptr must have 2B+1 entries")
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         if b > 0:
             common = (mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
@@ -299,7 +309,7 @@ def rank_metrics(gt, ge, k_values, per_query=True):
     recip = torch.empty((q, 1), dtype=torch.float32, device=dev) if per_query else None
     hits = torch.empty((q, len(ks)), dtype=torch.uint8, device=dev) if per_query else None
     sums = torch.empty(1 + len(ks), dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_rank_metrics(_ptr(gt), _ptr(ge), q, karr, len(ks), _ptr(recip), _ptr(hits), _ptr(sums), stream),
               "blp_rank_metrics")
@@ -317,7 +327,7 @@ def filter_index_build(edges, ent2idx, n_rows, num_rel):
     e = edges.shape[0]
     if ent2idx is not None:
         ent2idx = ent2idx.to(torch.int64).contiguous()
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         nbytes = int(lib().blp_filter_index_bytes(e))
         if nbytes < 0:
@@ -349,7 +359,7 @@ def filter_correct(model, ent, rel_weight, triples, out, lo, hi, index_ws, num_e
             raise ValueError(f"out[{name!r}] must be a contiguous (2, {T}) tensor")
         return ctypes.c_void_p(t.data_ptr() + lo * 4)
 
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_filter_correct(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
                                        ctypes.c_void_p(triples.data_ptr() + lo * 24), b, _ptr(h_rows), _ptr(t_rows),
@@ -372,7 +382,7 @@ def mrr_breakdown(recip, triples_ids, is_new=None, rel_categories=None):
     if rel_categories is not None:
         rel_categories = rel_categories.to(torch.int64).contiguous()
     out = torch.empty(18, dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_mrr_breakdown(_ptr(recip), t, t, _ptr(triples_ids), _ptr(is_new),
                                       is_new.numel() if is_new is not None else 0, _ptr(rel_categories),
@@ -389,7 +399,7 @@ def negative_sample(batch_size, num_negatives, repeats=1, *, device, seed=0, off
     if dev.type != "cuda":
         raise _lib.BlpError("blp_b200 runs on sm_100 CUDA devices only; there is no CPU fallback")
     storage = torch.empty((int(num_negatives), int(batch_size) * int(repeats), 2), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_negative_sample(int(batch_size), int(num_negatives), int(repeats), int(seed) & (2 ** 64 - 1),
                                         int(offset) & (2 ** 64 - 1), _ptr(storage), stream), "blp_negative_sample")
@@ -437,7 +447,7 @@ def train_loss(model, loss, ent_embs, rel_weight, rels, neg_idx, regularizer=0.0
         g_all = torch.empty(2 * b * d + rel_weight.numel(), dtype=torch.float32, device=dev)
         g_ent = g_all[:2 * b * d].view(b, 2, d)
         g_rel = g_all[2 * b * d:].view_as(rel_weight)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         idx, stream = _enter(dev)
         ws = _workspace(idx, stream.value, int(lib().blp_train_workspace_bytes(b, k)))
         check(lib().blp_train_loss(mid, lid, _ptr(ent_embs), _ptr(rel_weight), _ptr(rels), rel_weight.shape[0],
@@ -453,7 +463,7 @@ def scaled(x, scale_dev):
     x = _f32c(x)
     scale_dev = _f32c(scale_dev.reshape(1))
     y = torch.empty_like(x)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_scale(_ptr(y), _ptr(x), _ptr(scale_dev), x.numel(), stream), "blp_scale")
     return y
@@ -474,7 +484,7 @@ def pair_loss(loss, pos_scores, neg_scores, want_grad=False):
     out = torch.empty(1, dtype=torch.float32, device=dev)
     gp = torch.empty(b, dtype=torch.float32, device=dev) if want_grad else None
     gn = torch.empty((b, k), dtype=torch.float32, device=dev) if want_grad else None
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_pair_loss(lid, _ptr(pos), _ptr(neg), neg.stride(0) if b > 1 else k, b, k, _ptr(out), _ptr(gp),
                                   _ptr(gn), stream), "blp_pair_loss")
@@ -486,7 +496,7 @@ def l2_regularization(heads, tails, rels):
     dev = _require_cuda(heads, tails, rels)
     heads, tails, rels = (_f32c(x) for x in (heads, tails, rels))
     out = torch.empty(1, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_l2_regularization(_ptr(heads), heads.numel(), _ptr(tails), tails.numel(), _ptr(rels),
                                           rels.numel(), _ptr(out), stream), "blp_l2_regularization")
@@ -507,7 +517,7 @@ def pipe_probe(variant, device, n_threads=148 * 8 * 256, iters=4096):
     dev = torch.device(device)
     sink = torch.empty(n_threads, dtype=torch.float32, device=dev)
     ops = ctypes.c_double(0.0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         _, stream = _enter(dev)
         check(lib().blp_pipe_probe(int(variant), _ptr(sink), n_threads, iters, ctypes.byref(ops), stream), "blp_pipe_probe")
     return ops.value, sink

@@ -149,9 +149,14 @@ def _worker(rank, world, port, model, ret):
         lo, hi = shard_bounds(table.shape[0], world, rank)
         out = rank_sweep(model, table[lo:hi].contiguous(), torch.from_numpy(g["rel_weight"]), rows,
                          filter_index=fidx, filter_triples=g["triples"], chunk=40, ent_offset=lo,
-                         count_fn=oracle_count_fn)
+                         group=dist.group.WORLD, count_fn=oracle_count_fn)
         if rank == 0:
             ret.update({k: out[k].numpy() for k in ("gt", "ge", "gt_f", "ge_f")})
+        # group=None inside an initialised process group = NOT sharded (data-parallel replicas, bench.py --gpus N):
+        # no collective, every rank ranks its own triples against its own full table
+        mine = rows[rank::world]
+        local = rank_sweep(model, table, torch.from_numpy(g["rel_weight"]), mine, count_fn=oracle_count_fn)
+        ret[f"replica_gt_{rank}"] = local["gt"].numpy()
     finally:
         dist.destroy_process_group()
 
@@ -168,6 +173,8 @@ def test_sharded_sweep_equals_single_rank_gloo(model, world):
     mp.spawn(_worker, args=(world, _free_port(), model, ret), nprocs=world, join=True)
     for k in ("gt", "ge", "gt_f", "ge_f"):
         assert np.array_equal(ret[k], single[k].numpy()), k      # integer sums: bit-identical for any world size
+    for rank in range(world):
+        assert np.array_equal(ret[f"replica_gt_{rank}"], single["gt"].numpy()[:, rank::world]), rank
 
 
 def test_gather_rows_single_process_matches_index():

@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--eval-batch", type=int, default=1024, help="test triples ranked per step (E)")
     p.add_argument("--ref-eval-batch", type=int, default=128, help="E of the bounded CPU sample")
     p.add_argument("--mode", default="exact", choices=("exact", "fast"),
-                   help="eval sweep arithmetic: exact = reference fp32 order (bit-exact ranks); fast = tcgen05 3xTF32 "
+                   help="eval sweep arithmetic: exact = reference fp32 order (bit-exact ranks); fast = tcgen05 split-FP16 "
                         "contraction (distmult / complex / simple only, tolerance-classified)")
     p.add_argument("--eager-train", action="store_true",
                    help="run compute_loss forward+backward eagerly instead of replaying blp_b200.GraphedLossStep")
@@ -512,19 +512,19 @@ def main_b200(args):
     traffic = ncu_traffic(f"{kname}|{args.dataset}|E{e}|{args.mode}")
     share = statistics.mean(kern_ms) / statistics.mean(step_ms)
     if args.mode == "fast":
-        # tensor-core sweep: S = C (2E x 128) . E^T (128 x N); 3xTF32 issues three MMAs per algorithmic product
+        # tensor-core sweep: S = C (2E x 128) . E^T (128 x N); the split-FP16 form issues three MMAs per algorithmic product
         flops = 2.0 * (2 * e) * n * d
-        tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2.0
+        f16_peak = float(peaks.get("bf16_tflops", 2250.0))
         roofline = {
-            "bound": "tensor", "kernel": kname, "achieved": flops / kern_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": flops / kern_s / 1e12 / tf32_peak, "traffic": traffic,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate)" if peaks
-                            else "fallback 2250 / 2 TFLOP/s"),
+            "bound": "tensor", "kernel": kname, "achieved": flops / kern_s / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
+            "frac": flops / kern_s / 1e12 / f16_peak, "traffic": traffic,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (kind::f16 dense rate, cuBLAS 8192^3 burst)" if peaks
+                            else "fallback 2250 TFLOP/s"),
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
             "kernel_share_of_step": share,
-            "binding": "tcgen05 kind::tf32 with a 3xTF32 operand split (hi*hi + lo*hi + hi*lo): three MMAs are issued per "
-                       "algorithmic product, so frac <= 1/3 by construction; issued_frac is the tensor pipe's view",
-            "issued_tflops": 3 * flops / kern_s / 1e12, "issued_frac": 3 * flops / kern_s / 1e12 / tf32_peak,
+            "binding": "tcgen05 kind::f16 on split-FP16 operands (hi*hi + lo*hi + hi*lo, 22 significant bits): three MMAs "
+                       "are issued per algorithmic product, so frac <= 1/3 by construction; issued_frac is the tensor pipe's view",
+            "issued_tflops": 3 * flops / kern_s / 1e12, "issued_frac": 3 * flops / kern_s / 1e12 / f16_peak,
         }
     else:
         lane_ops_per = {"transe": 2.5, "distmult": 2.5, "complex": 5.0, "simple": 2.5}[args.model] * d  # head/tail mean
@@ -554,7 +554,7 @@ def main_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.mode == "exact" else "tf32x3 (fp32 accumulate; train step f32)", "data": "synthetic",
+        "dtype": "f32" if args.mode == "exact" else "f16x3 split of f32 (fp32 accumulate; train step f32)", "data": "synthetic",
         "config": config_dict(args, w, e, flush),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

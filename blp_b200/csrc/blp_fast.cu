@@ -9,37 +9,57 @@
 // NOT bit-exact by construction; it is opt-in and its parity is tolerance-classified:
 // |score_fast - score_ref| <= 1e-5 * sum|terms|, rank differences only inside that band.
 //
-// Arithmetic: 3xTF32.  Every fp32 operand x is split as x = hi + lo with hi = tf32(x), lo = tf32(x - hi)
-// (cvt.rna), and hi*hi + lo*hi + hi*lo is accumulated in fp32 in TMEM: ~2^-21 relative per product.
+// Arithmetic: split-FP16 ("3xFP16").  Every fp32 operand x is scaled by a power of two s (exact) and split as
+// s*x = hi + lo with hi = fp16(s*x), lo = fp16(s*x - hi): 22 significant bits, the same as the classic 3xTF32
+// split, but kind::f16 runs at twice the kind::tf32 rate and the operands take half the bytes.
+// hi*hi + lo*hi + hi*lo is accumulated in fp32 in TMEM (the dropped lo*lo term is ~2^-22 relative).  The scales
+// keep fp16 in range for any input magnitude: one per entity table (max |e| -> 2^14, blp_fast_prepare_table) and
+// one per query row (max |c_q| -> 2^14, fold kernel); the epilogue compares the raw accumulator against the true
+// score pre-multiplied by (s_table * s_query), so no per-score rescaling is needed.
 //
-// Kernel (sm_100a, one persistent CTA per SM, 256 threads):
-//   warp 0 lane 0   TMA producer: query tile (hi | lo, 128 KB, resident per M tile) and a 3-stage ring of
-//                   candidate K-blocks (hi | lo boxes of 128 rows x 32 floats, 128-byte swizzle)
-//   warp 1 lane 0   tcgen05.mma issuer (kind::tf32, M = 128 queries, N = 128 candidates, K = 8 per
-//                   instruction, 48 instructions per tile), accumulators double-buffered in TMEM
-//   warp 2          TMEM allocation (256 columns)
-//   warps 4-7       epilogue: tcgen05.ld 32 columns at a time -- TMEM lane = query row, so each thread owns
-//                   one query -- compare against the true score, count, one atomicAdd pair per query and
-//                   M-tile run.  No score ever leaves the SM.
+// Kernel (sm_100a, one persistent CTA per SM, 384 threads).  A work item is (256 queries) x (128 candidates):
+//   warp 0 lane 0   TMA producer: the query block (2 halves x [hi | lo], 128 KB, resident while the CTA stays on
+//                   the same 256 queries) and a 3-stage ring of candidate k-blocks ([hi | lo] boxes of 128 rows x
+//                   64 halves, 128-byte swizzle)
+//   warp 1 lane 0   tcgen05.mma issuer (kind::f16, M = 128, N = 128, K = 16): every candidate k-block is used by
+//                   BOTH 128-query halves (two accumulators), which halves the L2 -> SMEM bytes per flop -- at one
+//                   half per CTA the kernel is bound by L2 bandwidth, not by the tensor pipe; accumulators are
+//                   double-buffered in TMEM (2 buffers x 2 halves x 128 columns = all 512 columns)
+//   warp 2          TMEM allocation
+//   warps 4-11      epilogue: tcgen05.ld 32 columns at a time -- TMEM lane = query row, so each thread owns one
+//                   query of each half; the two warps of a lane quarter split the column chunks -- compare against
+//                   the scaled true score, count, one atomicAdd pair per query and query-block run.  No score
+//                   ever leaves the SM.
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "blp_sweep.h"
 
 namespace blp {
 
-constexpr int kFM = 128, kFN = 128;
-constexpr int kFStages = 3;
-constexpr int kFBox = 128 * 32;            // floats in one TMA box (128 rows x 32 floats = 16 KB)
-constexpr int kFThreads = 256;
-constexpr int kTmemCols = 256;             // two 128-column accumulators
+#ifndef BLP_FAST_N
+#define BLP_FAST_N 128
+#endif
+constexpr int kFM = 128, kFN = BLP_FAST_N; // rows per MMA (TMEM lanes), candidates per work item
+constexpr int kFH = 2;                     // 128-query halves per work item
+constexpr int kFBufs = 512 / (kFH * kFN);  // accumulator buffers in TMEM (all 512 columns)
+constexpr int kFStages = 3 * 128 / kFN;    // candidate k-block ring (96 KB)
+constexpr int kFKB = 64;                   // halves per k-block (one 128-byte swizzle span)
+constexpr int kFBox = 128 * kFKB;          // halves in one query TMA box (128 rows x 64 halves = 16 KB)
+constexpr int kFBoxB = kFN * kFKB;         // halves in one candidate TMA box (kFN rows x 64 halves)
+constexpr int kFEpiWarps = 8;                // epilogue warps: two per TMEM lane quarter, they split the column chunks
+constexpr int kFThreads = (4 + kFEpiWarps) * 32;
+constexpr int kTmemCols = 512;             // kFBufs buffers x 2 halves x kFN columns
+constexpr float kFTargetExp = 14.0f;       // operands are scaled so that max |x| <= 2^14 (fp16 max is 65504)
 
 struct __align__(1024) FastSmem {
-    float a[2][4][kFBox];                  // [hi | lo][k-block] query tile
-    float b[kFStages][2][kFBox];           // [stage][hi | lo] candidate k-block
+    __half a[kFH][2][2][kFBox];            // [query half][hi | lo][k-block] query block
+    __half b[kFStages][2][kFBoxB];         // [stage][hi | lo] candidate k-block
     uint64_t a_full, a_empty;
     uint64_t b_full[kFStages], b_empty[kFStages];
-    uint64_t d_full[2], d_empty[2];
+    uint64_t d_full[kFBufs], d_empty[kFBufs];
     uint32_t tmem_base;
 };
 
@@ -49,9 +69,11 @@ struct FastArgs {
     long long m_tiles, n_tiles;
     const float *true_score;               // indexed by output slot
     const long long *self_id;              // [q_pad] global candidate id of the query's true entity (-1 = padding)
+    const float *qscale;                   // [q_pad] s_table * s_query of every query row (powers of two)
     int *gt, *ge;
     float *scores_out;                     // optional (2b, ld_scores) matrix of the fast scores (verification aid)
     long long ld_scores;
+    int debug;                             // timing experiments (BLP_FAST_DEBUG): 1 = no epilogue work, 2 = no B loads, 4 = no MMAs
 };
 
 // ---- PTX wrappers (tcgen05) ---------------------------------------------------------------------
@@ -64,11 +86,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] . B[smem desc]^T, tf32 inputs, fp32 accumulation
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, fp16 inputs, fp32 accumulation
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -90,7 +112,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile of [rows][32 floats] written by TMA with the 128-byte swizzle: 8-row groups are
+// K-major operand tile of [rows][64 halves] written by TMA with the 128-byte swizzle: 8-row groups are
 // 1024 bytes apart (SBO), the leading-dimension offset is unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t umma_smem_desc(const void *p) {
     uint64_t d = (uint64_t)((smem_u32(p) & 0x3FFFFu) >> 4);   // start address, 16-byte units
@@ -100,15 +122,23 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void *p) {
     d |= (uint64_t)2 << 61;                                    // SWIZZLE_128B
     return d;
 }
-// kind::tf32, fp32 accumulator, both operands K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 with fp16 operands (format 0), fp32 accumulator (format 1), both operands K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// power-of-two scale that maps max_abs to at most 2^14 (1 when the operand is all zeros / not finite)
+__device__ __forceinline__ float pow2_scale(float max_abs) {
+    if (!(max_abs > 0.0f) || !(max_abs < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(max_abs, &e);                                  // max_abs = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, (int)kFTargetExp - e);
+}
+// s*x = hi + lo, both fp16 (round to nearest even); s is a power of two, so s*x is exact
+__device__ __forceinline__ void split_f16(float x, float s, __half &hi, __half &lo) {
+    const float v = fmul(x, s);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(fsub(v, __half2float(hi)));
 }
 
 // v[idx] for a runtime idx without spilling v to local memory: a 5-level select tree on the index bits
@@ -126,19 +156,46 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int idx) {
 }
 
 // ---- operand preparation --------------------------------------------------------------------------
-// Split table: rows [0, n_pad) = tf32(e), rows [n_pad, 2 n_pad) = tf32(e - tf32(e)); rows >= n_local are zero.
-__global__ void split_table_kernel(const float4 *__restrict__ ent, long long n_local, long long n_pad, float4 *__restrict__ out) {
+// Table workspace: [n_pad rows x 128] fp16 hi, [n_pad x 128] fp16 lo, then a 256-byte header {float scale;
+// uint max_abs_bits}.  Rows >= n_local are zero.
+struct FastTableHeader {
+    float scale;
+    unsigned int max_bits;
+};
+
+__global__ void table_maxabs_kernel(const float4 *__restrict__ ent, long long total4, unsigned int *__restrict__ max_bits) {
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(ent + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_bits, __float_as_uint(m));   // non-negative floats order like uints
+}
+
+__global__ void split_table_kernel(const float4 *__restrict__ ent, long long n_local, long long n_pad,
+                                   __half *__restrict__ out, FastTableHeader *__restrict__ hdr) {
+    const float s = pow2_scale(__uint_as_float(hdr->max_bits));
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->scale = s;
     const long long total = n_pad * (kD / 4);
+    uint2 *hi_out = reinterpret_cast<uint2 *>(out), *lo_out = reinterpret_cast<uint2 *>(out + n_pad * kD);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / (kD / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < n_local) v = __ldg(ent + i);
-        float4 hi, lo;
-        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-        lo.x = tf32_rna(fsub(v.x, hi.x)); lo.y = tf32_rna(fsub(v.y, hi.y));
-        lo.z = tf32_rna(fsub(v.z, hi.z)); lo.w = tf32_rna(fsub(v.w, hi.w));
-        out[i] = hi;
-        out[total + i] = lo;
+        __half h[4], l[4];
+        split_f16(v.x, s, h[0], l[0]);
+        split_f16(v.y, s, h[1], l[1]);
+        split_f16(v.z, s, h[2], l[2]);
+        split_f16(v.w, s, h[3], l[3]);
+        uint2 ph, pl;
+        ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        hi_out[i] = ph;
+        lo_out[i] = pl;
     }
 }
 
@@ -168,8 +225,10 @@ __device__ __forceinline__ float fold_coeff(bool head_pred, const float *__restr
 template <int MODEL>
 __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const RowRef tr, const RowRef rr,
                                                           const long long *__restrict__ triples, long long b,
-                                                          long long q_pad, float *__restrict__ qsplit,
-                                                          long long *__restrict__ self_id) {
+                                                          long long q_pad, __half *__restrict__ qsplit,
+                                                          long long *__restrict__ self_id, float *__restrict__ qscale,
+                                                          const FastTableHeader *__restrict__ table_hdr) {
+    __shared__ float s_max[kD / 32];
     const long long q = blockIdx.x;
     const int j = threadIdx.x;
     float c = 0.0f;
@@ -180,10 +239,22 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
         c = fold_coeff<MODEL>(head_pred, hr.row(i, kD), tr.row(i, kD), rr.row(i, kD), j);
         self = triples[i * 3 + (head_pred ? 0 : 1)];
     }
-    const float hi = tf32_rna(c);
+    // per-row power-of-two scale from the row's max |c|
+    float m = fabsf(c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((j & 31) == 0) s_max[j >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3]));
+    const float sq = pow2_scale(m);
+    __half hi, lo;
+    split_f16(c, sq, hi, lo);
     qsplit[q * kD + j] = hi;
-    qsplit[(q_pad + q) * kD + j] = tf32_rna(fsub(c, hi));
-    if (j == 0) self_id[q] = self;
+    qsplit[(q_pad + q) * kD + j] = lo;
+    if (j == 0) {
+        self_id[q] = self;
+        qscale[q] = fmul(sq, table_hdr->scale);
+    }
 }
 
 // ---- the sweep --------------------------------------------------------------------------------------
@@ -200,9 +271,9 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
             mbar_init(&sm.b_full[s], 1);
             mbar_init(&sm.b_empty[s], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kFBufs; ++i) {
             mbar_init(&sm.d_full[i], 1);
-            mbar_init(&sm.d_empty[i], 4);        // one arrival per epilogue warp
+            mbar_init(&sm.d_empty[i], kFEpiWarps);   // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -212,9 +283,11 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    // this CTA's share of the (M tile, N tile) list, N fastest so the query tile stays resident
+    // this CTA's share of the (query block, candidate tile) list, candidates fastest so the query block stays resident
     const long long total = args.m_tiles * args.n_tiles;
     const long long id_begin = total * blockIdx.x / gridDim.x, id_end = total * (blockIdx.x + 1) / gridDim.x;
+    // 128-query halves of query block m that hold real queries (the last block may have one)
+    auto halves_of = [&](long long m) -> int { return (2 * args.b - m * (kFH * kFM) > kFM) ? 2 : 1; };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -225,22 +298,26 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 const long long m = id / args.n_tiles, n = id % args.n_tiles;
                 if (m != cur_m) {
                     mbar_wait(&sm.a_empty, (a_use & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&sm.a_full, 2 * 4 * kFBox * 4);
+                    mbar_arrive_expect_tx(&sm.a_full, kFH * 2 * 2 * kFBox * 2);
 #pragma unroll
-                    for (int hl = 0; hl < 2; ++hl)
+                    for (int half = 0; half < kFH; ++half)
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb)
-                            tma_tensor2d_g2s(&sm.a[hl][kb][0], &tm_q, kb * 32, (int)(hl * args.q_pad + m * kFM), &sm.a_full);
+                        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+                                tma_tensor2d_g2s(&sm.a[half][hl][kb][0], &tm_q, kb * kFKB,
+                                                 (int)(hl * args.q_pad + m * (kFH * kFM) + half * kFM), &sm.a_full);
                     ++a_use;
                     cur_m = m;
                 }
-                for (int kb = 0; kb < 4; ++kb, ++kbit) {
+                for (int kb = 0; kb < 2; ++kb, ++kbit) {
                     const int stage = kbit % kFStages;
                     const uint32_t use = kbit / kFStages;
                     mbar_wait(&sm.b_empty[stage], (use & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&sm.b_full[stage], 2 * kFBox * 4);
-                    tma_tensor2d_g2s(&sm.b[stage][0][0], &tm_e, kb * 32, (int)(n * kFN), &sm.b_full[stage]);
-                    tma_tensor2d_g2s(&sm.b[stage][1][0], &tm_e, kb * 32, (int)(args.n_pad + n * kFN), &sm.b_full[stage]);
+                    if ((args.debug & 2) && kbit >= kFStages) { mbar_arrive(&sm.b_full[stage]); continue; }
+                    mbar_arrive_expect_tx(&sm.b_full[stage], 2 * kFBoxB * 2);
+                    tma_tensor2d_g2s(&sm.b[stage][0][0], &tm_e, kb * kFKB, (int)(n * kFN), &sm.b_full[stage]);
+                    tma_tensor2d_g2s(&sm.b[stage][1][0], &tm_e, kb * kFKB, (int)(args.n_pad + n * kFN), &sm.b_full[stage]);
                 }
             }
         }
@@ -248,33 +325,37 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = umma_idesc_tf32(kFM, kFN);
+            constexpr uint32_t idesc = umma_idesc_f16(kFM, kFN);
             long long cur_m = -1;
             uint32_t a_use = 0, kbit = 0, it = 0;
+            int halves = kFH;
             for (long long id = id_begin; id < id_end; ++id, ++it) {
                 const long long m = id / args.n_tiles;
                 if (m != cur_m) {
                     mbar_wait(&sm.a_full, a_use & 1u);
                     ++a_use;
                     cur_m = m;
+                    halves = halves_of(m);
                 }
-                const uint32_t buf = it & 1u, duse = it >> 1;
-                mbar_wait(&sm.d_empty[buf], (duse & 1u) ^ 1u);          // epilogue has drained this accumulator
+                const uint32_t buf = it % kFBufs, duse = it / kFBufs;
+                mbar_wait(&sm.d_empty[buf], (duse & 1u) ^ 1u);          // epilogue has drained these accumulators
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + buf * kFN;
-                for (int kb = 0; kb < 4; ++kb, ++kbit) {
+                for (int kb = 0; kb < 2; ++kb, ++kbit) {
                     const int stage = kbit % kFStages;
                     const uint32_t use = kbit / kFStages;
                     mbar_wait(&sm.b_full[stage], use & 1u);
                     tc_fence_after();
-                    const uint64_t a_hi = umma_smem_desc(&sm.a[0][kb][0]), a_lo = umma_smem_desc(&sm.a[1][kb][0]);
                     const uint64_t b_hi = umma_smem_desc(&sm.b[stage][0][0]), b_lo = umma_smem_desc(&sm.b[stage][1][0]);
+                    for (int half = 0; half < ((args.debug & 4) ? 0 : halves); ++half) {   // the candidate k-block serves both query halves
+                        const uint32_t d_tmem = tmem + buf * (kFH * kFN) + half * kFN;
+                        const uint64_t a_hi = umma_smem_desc(&sm.a[half][0][kb][0]), a_lo = umma_smem_desc(&sm.a[half][1][kb][0]);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {                    // 8 tf32 = 32 bytes = 2 descriptor units per step
-                        const uint64_t o = (uint64_t)(ks * 2);
-                        umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kb | ks) != 0);
-                        umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+                        for (int ks = 0; ks < kFKB / 16; ++ks) {        // 16 halves = 32 bytes = 2 descriptor units per step
+                            const uint64_t o = (uint64_t)(ks * 2);
+                            umma_f16(d_tmem, a_lo + o, b_hi + o, idesc, (kb | ks) != 0);
+                            umma_f16(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+                            umma_f16(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+                        }
                     }
                     umma_commit(&sm.b_empty[stage]);                    // frees the stage once these MMAs have read it
                 }
@@ -284,76 +365,102 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue: one query row per thread =====================
-        const int ew = warp & 3, row = ew * 32 + lane;
-        long long cur_m = -1, slot = -1, self_local = -1;
-        float st = 0.0f;
-        bool valid_q = false;
-        int cgt = 0, cge = 0;
+        // ===================== epilogue: one query row of each half per thread =====================
+        // TMEM lane = query row; a warp can only read the lane quarter (warp % 4), so the two warps of a quarter
+        // split the 32-column chunks between them (chunk parity = part)
+        const int ew = warp & 3, part = (warp - 4) >> 2, row = ew * 32 + lane;
+        long long cur_m = -1;
+        long long slot[kFH], self_local[kFH];
+        float th[kFH], inv[kFH];                                         // scaled true score, 1 / scale
+        bool valid_q[kFH];
+        int cgt[kFH], cge[kFH];
+        int halves = kFH;
+#pragma unroll
+        for (int h = 0; h < kFH; ++h) { slot[h] = -1; self_local[h] = -1; th[h] = 0.f; inv[h] = 1.f; valid_q[h] = false; cgt[h] = cge[h] = 0; }
         uint32_t it = 0;
         auto flush = [&]() {
-            if (valid_q && (cgt | cge)) {
-                atomicAdd(&args.gt[slot], cgt);
-                atomicAdd(&args.ge[slot], cge);
+#pragma unroll
+            for (int h = 0; h < kFH; ++h) {
+                if (valid_q[h] && (cgt[h] | cge[h])) {
+                    atomicAdd(&args.gt[slot[h]], cgt[h]);
+                    atomicAdd(&args.ge[slot[h]], cge[h]);
+                }
+                cgt[h] = cge[h] = 0;
             }
-            cgt = cge = 0;
         };
         for (long long id = id_begin; id < id_end; ++id, ++it) {
             const long long m = id / args.n_tiles, n = id % args.n_tiles;
             if (m != cur_m) {
                 flush();
-                const long long q = m * kFM + row;
-                valid_q = q < 2 * args.b;
-                if (valid_q) {
-                    slot = q < args.b ? q : args.tail_off + (q - args.b);
-                    st = args.true_score[slot];
-                    self_local = args.self_id[q] - args.ent_offset;
-                    valid_q = st == st;                                  // NaN = flagged triple (bad index)
+                halves = halves_of(m);
+#pragma unroll
+                for (int h = 0; h < kFH; ++h) {
+                    const long long q = m * (kFH * kFM) + h * kFM + row;
+                    valid_q[h] = q < 2 * args.b;
+                    if (valid_q[h]) {
+                        slot[h] = q < args.b ? q : args.tail_off + (q - args.b);
+                        const float st = args.true_score[slot[h]];
+                        const float qs = args.qscale[q];
+                        th[h] = fmul(st, qs);                            // power-of-two scale: exact
+                        inv[h] = __frcp_rn(qs);
+                        self_local[h] = args.self_id[q] - args.ent_offset;
+                        valid_q[h] = st == st;                           // NaN = flagged triple (bad index)
+                    }
                 }
                 cur_m = m;
             }
-            const uint32_t buf = it & 1u, duse = it >> 1;
+            const uint32_t buf = it % kFBufs, duse = it / kFBufs;
             mbar_wait(&sm.d_full[buf], duse & 1u);
             tc_fence_after();
             const long long tile_base = n * kFN;
             const int nvalid = (int)min((long long)kFN, args.n_local - tile_base);
-            const long long self_col = self_local - tile_base;           // column of the true entity, if in this tile
-            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + buf * kFN;
+#pragma unroll
+            for (int h = 0; h < kFH; ++h) {
+                if (h >= halves || (args.debug & 1)) continue;           // uniform over the CTA
+                const long long self_col = self_local[h] - tile_base;    // column of the true entity, if in this tile
+                const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + buf * (kFH * kFN) + h * kFN;
+                const float st = th[h];
+                const long long q = m * (kFH * kFM) + h * kFM + row;
 #pragma unroll 1
-            for (int ch = 0; ch < kFN / 32; ++ch) {
-                uint32_t v[32];
-                __syncwarp();                                            // the TMEM load is warp-collective
-                tmem_ld32(taddr + ch * 32, v);
-                tmem_ld_wait();
-                if (args.scores_out && m * kFM + row < 2 * args.b) {
-                    float *orow = args.scores_out + (m * kFM + row) * args.ld_scores + tile_base + ch * 32;
+                for (int ch = part; ch < kFN / 32; ch += kFEpiWarps / 4) {
+                    uint32_t v[32];
+                    __syncwarp();                                        // the TMEM load is warp-collective
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (args.scores_out && q < 2 * args.b) {
+                        float *orow = args.scores_out + q * args.ld_scores + tile_base + ch * 32;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (ch * 32 + c < nvalid) orow[c] = __uint_as_float(v[c]);
-                }
-                if (valid_q) {
-                    if (nvalid == kFN) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float s = __uint_as_float(v[c]);
-                            cgt += s > st;
-                            cge += s >= st;
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float s = __uint_as_float(v[c]);
-                            const bool ok = ch * 32 + c < nvalid;
-                            cgt += ok && s > st;
-                            cge += ok && s >= st;
-                        }
+                        for (int c = 0; c < 32; ++c)
+                            if (ch * 32 + c < nvalid) orow[c] = fmul(__uint_as_float(v[c]), inv[h]);
                     }
-                    if (self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
-                        // the true entity itself: it ties with s_true by definition (utils.py:104-105), whatever
-                        // the fast arithmetic produced for it
-                        const float s_self = __uint_as_float(select32(v, (int)(self_col & 31)));
-                        cgt -= s_self > st;
-                        cge += 1 - (s_self >= st);
+                    if (valid_q[h]) {
+                        int g[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};    // independent chains
+                        if (nvalid == kFN) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float s = __uint_as_float(v[c]);
+                                g[c & 3] += s > st;
+                                e[c & 3] += s >= st;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float s = __uint_as_float(v[c]);
+                                const bool ok = ch * 32 + c < nvalid;
+                                g[c & 3] += ok && s > st;
+                                e[c & 3] += ok && s >= st;
+                            }
+                        }
+                        int gs = (g[0] + g[1]) + (g[2] + g[3]), es = (e[0] + e[1]) + (e[2] + e[3]);
+                        if (self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
+                            // the true entity itself: it ties with s_true by definition (utils.py:104-105), whatever
+                            // the fast arithmetic produced for it
+                            const float s_self = __uint_as_float(select32(v, (int)(self_col & 31)));
+                            gs -= s_self > st;
+                            es += 1 - (s_self >= st);
+                        }
+                        cgt[h] += gs;
+                        cge[h] += es;
                     }
                 }
             }
@@ -384,34 +491,46 @@ static EncodeTiledFn fast_encode_fn() {
     }();
     return fn;
 }
-// [rows][128 floats] viewed as boxes of [128 rows][32 floats], 128-byte swizzle
-static bool make_rows_tmap(CUtensorMap *tm, const void *base, long long rows) {
+// [rows][128 halves] viewed as boxes of [box_rows rows][64 halves], 128-byte swizzle
+static bool make_rows_tmap(CUtensorMap *tm, const void *base, long long rows, int box_rows) {
     EncodeTiledFn enc = fast_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)kD * 4};
-    const cuuint32_t box[2] = {32, 128};
+    const cuuint64_t strides[1] = {(cuuint64_t)kD * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kFKB, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-long long fast_table_ws_bytes(long long n_local) { return 2 * round_up(n_local > 0 ? n_local : 1, kFN) * kD * 4; }
+// table: hi + lo halves of n_pad rows, then the header
+long long fast_table_ws_bytes(long long n_local) { return 2 * round_up(n_local > 0 ? n_local : 1, kFN) * kD * 2 + 256; }
+// queries: hi + lo halves of q_pad rows, self ids, scales
 long long fast_query_ws_bytes(long long t) {
-    const long long q_pad = round_up(2 * (t > 0 ? t : 1), kFM);
-    return 2 * q_pad * kD * 4 + q_pad * 8;
+    const long long q_pad = round_up(2 * (t > 0 ? t : 1), kFH * kFM);
+    return 2 * q_pad * kD * 2 + q_pad * 8 + q_pad * 4;
 }
 
 int fast_prepare_table(const float *ent, long long n_local, void *table_ws, cudaStream_t st) {
     const long long n_pad = round_up(n_local > 0 ? n_local : 1, kFN);
+    __half *out = reinterpret_cast<__half *>(table_ws);
+    FastTableHeader *hdr = reinterpret_cast<FastTableHeader *>(out + 2 * n_pad * kD);
+    BLP_CUDA(cudaMemsetAsync(hdr, 0, sizeof(FastTableHeader), st));
+    const long long total4 = n_local * (kD / 4);
+    if (total4 > 0) {
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        table_maxabs_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(ent), total4, &hdr->max_bits);
+        count_launch();
+        BLP_CUDA(cudaGetLastError());
+    }
     const long long total = n_pad * (kD / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_table_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(ent), n_local, n_pad,
-                                                         reinterpret_cast<float4 *>(table_ws));
+    split_table_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(ent), n_local, n_pad, out, hdr);
     count_launch();
     return check_cuda(cudaGetLastError(), "split_table_kernel launch");
 }
@@ -433,17 +552,24 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     }
     FastArgs a{};
     a.n_local = n_local; a.ent_offset = ent_offset; a.n_pad = round_up(n_local, kFN);
-    a.b = b; a.tail_off = tail_off; a.q_pad = round_up(2 * b, kFM);
-    a.m_tiles = a.q_pad / kFM; a.n_tiles = a.n_pad / kFN;
-    float *qsplit = reinterpret_cast<float *>(query_ws);
+    a.b = b; a.tail_off = tail_off; a.q_pad = round_up(2 * b, kFH * kFM);
+    a.m_tiles = a.q_pad / (kFH * kFM); a.n_tiles = a.n_pad / kFN;
+    __half *qsplit = reinterpret_cast<__half *>(query_ws);
     long long *self_id = reinterpret_cast<long long *>(qsplit + 2 * a.q_pad * kD);
-    a.true_score = true_score; a.self_id = self_id; a.gt = gt; a.ge = ge;
+    float *qscale = reinterpret_cast<float *>(self_id + a.q_pad);
+    const __half *table = reinterpret_cast<const __half *>(table_ws);
+    const FastTableHeader *hdr = reinterpret_cast<const FastTableHeader *>(table + 2 * a.n_pad * kD);
+    a.true_score = true_score; a.self_id = self_id; a.qscale = qscale; a.gt = gt; a.ge = ge;
     a.scores_out = scores_out; a.ld_scores = ld_scores;
+    {
+        const char *e = getenv("BLP_FAST_DEBUG");
+        a.debug = e ? atoi(e) : 0;
+    }
 
     switch (model) {
-    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id); break;
-    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id); break;
-    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id); break;
+    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
+    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
+    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
     }
     count_launch();
     BLP_CUDA(cudaGetLastError());
@@ -451,7 +577,7 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     CUtensorMap tm_q, tm_e;
     memset(&tm_q, 0, sizeof(tm_q));
     memset(&tm_e, 0, sizeof(tm_e));
-    if (!make_rows_tmap(&tm_q, qsplit, 2 * a.q_pad) || !make_rows_tmap(&tm_e, table_ws, 2 * a.n_pad)) {
+    if (!make_rows_tmap(&tm_q, qsplit, 2 * a.q_pad, kFM) || !make_rows_tmap(&tm_e, table_ws, 2 * a.n_pad, kFN)) {
         set_error("cuTensorMapEncodeTiled failed for the fast-mode operand tables");
         return BLP_ECUDA;
     }

@@ -80,7 +80,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 other row blocks (one all-reduce of the counters per sweep); group=None = not sharded
     h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
     mode        "exact" (default): every score carries the reference's fp32 roundings, ranks are bit-exact;
-                "fast": distmult / complex / simple at D = 128 as a 3xTF32 tensor-core contraction
+                "fast": distmult / complex / simple at D = 128 as a split-FP16 tensor-core contraction
                 (blp_rank_sweep_fast) -- scores within ~1e-6 * sum|terms|, ranks may differ for candidates
                 inside that band around the true score; `fast_table` = ops.fast_table(ent_emb) to reuse
                 the split table across calls

@@ -125,13 +125,14 @@ int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_off
 /* ---- tensor-core ("fast") mode of the sweep: distmult / complex / simple, d = 128 ----
  * The bilinear scores are linear in the candidate row once the query side is folded
  * (models.py:226-248 with the candidate factored out), so the sweep is a (2t x 128) x (128 x n)
- * contraction: tcgen05.mma kind::tf32 with a 3xTF32 operand split (hi*hi + lo*hi + hi*lo, fp32
- * accumulation in TMEM) and the rank-count epilogue reading TMEM.  NOT bit-exact (folding and
- * the summation order differ from models.py:227): scores agree to ~1e-6 * sum|terms| and ranks
- * differ only for candidates inside that band around the true score.  The true score itself
- * is the exact one, and the true entity always counts as a tie (utils.py:104-105).
+ * contraction: tcgen05.mma kind::f16 on split-FP16 operands (x scaled by a power of two, then hi = fp16(x),
+ * lo = fp16(x - hi); hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM -- 22 significant bits, like
+ * 3xTF32 at twice the MMA rate and half the operand bytes) and the rank-count epilogue reading TMEM.
+ * NOT bit-exact (folding and the summation order differ from models.py:227): scores agree to
+ * ~1e-6 * sum|terms| and ranks differ only for candidates inside that band around the true score.
+ * The true score itself is the exact one, and the true entity always counts as a tie (utils.py:104-105).
  *   table_ws   blp_fast_table_bytes(n_local) bytes, filled by blp_fast_prepare_table (once per
- *              table); query_ws  blp_fast_query_bytes(t) bytes of scratch
+ *              table: max-|e| scale + split); query_ws  blp_fast_query_bytes(t) bytes of scratch
  *   scores_out optional (2t, ld_scores) matrix receiving the fast scores (row q: head queries
  *              then tail queries; column: local candidate) -- verification aid, NULL normally
  * Other arguments as blp_rank_sweep. */

@@ -1,4 +1,4 @@
-"""Tensor-core (tcgen05, 3xTF32) mode of the eval sweep vs the oracle: tolerance-classified parity.
+"""Tensor-core (tcgen05, split-FP16) mode of the eval sweep vs the oracle: tolerance-classified parity.
 
 The fast mode folds the query side (r*t, h*r, ...) and sums in tensor-core order, so it cannot carry the
 reference's fp32 roundings (models.py:227 association).  Contract (north_star "scores within

@@ -1,0 +1,120 @@
+"""BASELINE.json configs at their full sizes, through size-independent properties plus oracle checks on the
+queries the oracle can finish in seconds:
+  configs[3]  WN18RR-sized (40,943 entities) BLP-ComplEx full-entity sweep, exact and tensor-core mode
+  configs[4]  one 8-way shard of the Wikidata5M-scale table (600,000 rows) BLP-TransE at the reference's
+              eval batch of 2 (the HBM-bound register-tile shape), with ent_offset / shard sums
+  train       B = 1024, K = 512 (the reference's Wikidata5M training batch) against the oracle
+and the degenerate shapes (T = 0, K = 0)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+
+import blp_b200
+from blp_b200 import ops
+from test_gpu_eval import make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_wn18rr_complex_full_entity_sweep(cuda_device):
+    model, n, b = "complex", 40943, 64                                  # reference eval_batch_size = 64
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=17, n_rel=11)
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    full = blp_b200.rank_sweep(model, e, r, triples)
+    assert bool((full["gt"] < full["ge"]).all())                        # the true entity ties itself
+    # oracle on every 8th triple (16 queries x 40,943 candidates)
+    sel = torch.arange(0, b, 8)
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads[sel]].numpy(), ent[tails[sel]].numpy(), rel[rels[sel]].numpy(),
+                            heads[sel].numpy(), tails[sel].numpy())
+    k = len(sel)
+    assert np.array_equal(full["gt"].cpu()[:, sel].reshape(-1).numpy(), co["gt"])
+    assert np.array_equal(full["ge"].cpu()[:, sel].reshape(-1).numpy(), co["ge"])
+    assert np.array_equal(full["true_score"].cpu()[:, sel].reshape(-1).numpy(), co["true_score"]) and k == 8
+    # candidate order does not matter; shard sums are exact
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).to(dev)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device=dev)
+    tp = torch.stack([inv[triples[:, 0]], inv[triples[:, 1]], triples[:, 2]], dim=1)
+    shuffled = blp_b200.rank_sweep(model, e[perm].contiguous(), r, tp)
+    assert torch.equal(shuffled["gt"], full["gt"]) and torch.equal(shuffled["ge"], full["ge"])
+    acc = None
+    for s in range(3):
+        lo, hi = blp_b200.shard_bounds(n, 3, s)
+        part = blp_b200.rank_sweep(model, e[lo:hi].contiguous(), r, triples, ent_offset=lo,
+                                   h_rows=e[triples[:, 0]], t_rows=e[triples[:, 1]])
+        cur = torch.stack([part["gt"], part["ge"]])
+        acc = cur if acc is None else acc + cur
+    assert torch.equal(acc[0], full["gt"]) and torch.equal(acc[1], full["ge"])
+    # tensor-core mode: same true scores, ranks equal except inside the tolerance band
+    fast = blp_b200.rank_sweep(model, e, r, triples, mode="fast")
+    assert torch.equal(fast["true_score"], full["true_score"])
+    assert ((fast["gt"] == full["gt"]) & (fast["ge"] == full["ge"])).float().mean().item() >= 0.95
+    assert int((fast["gt"] - full["gt"]).abs().max()) <= 3
+    assert abs(blp_b200.finalize(fast)["mrr"] - blp_b200.finalize(full)["mrr"]) <= 1e-6
+
+
+def test_wikidata5m_shard_transe_eval_batch_2(cuda_device):
+    model, n_shard, b, offset = "transe", 600_000, 2, 1_200_000          # rank 2 of 8: rows [1.2 M, 1.8 M)
+    g = torch.Generator().manual_seed(23)
+    shard = torch.nn.functional.normalize(torch.randn(n_shard, 128, generator=g), dim=-1)
+    rel = (torch.rand(822, 128, generator=g) * 2 - 1) * (6.0 / (822 + 128)) ** 0.5
+    # one true head lives in this shard, the other rows come from other ranks (passed pre-gathered)
+    h_rows = torch.stack([shard[12345], torch.nn.functional.normalize(torch.randn(128, generator=g), dim=-1)])
+    t_rows = torch.nn.functional.normalize(torch.randn(2, 128, generator=g), dim=-1)
+    triples = torch.tensor([[offset + 12345, 7, 3], [4_000_000, 99, 800]])
+    dev = cuda_device
+    out = blp_b200.rank_sweep(model, shard.to(dev), rel.to(dev), triples.to(dev), ent_offset=offset,
+                              h_rows=h_rows.to(dev), t_rows=t_rows.to(dev), chunk=2)
+    co = c_oracle.eval_rank(model, shard.numpy(), h_rows.numpy(), t_rows.numpy(), rel[triples[:, 2]].numpy(),
+                            None, None)                   # true rows = the query rows themselves (sharded caller)
+    assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+    assert np.array_equal(out["gt"].reshape(-1).cpu().numpy(), co["gt"])
+    assert np.array_equal(out["ge"].reshape(-1).cpu().numpy(), co["ge"])
+    # the head query of triple 0 scans its own true row in this shard: ge counts the self-match, gt does not
+    assert int(out["ge"][0, 0]) >= int(out["gt"][0, 0]) + 1
+    # sub-shards add up
+    a = blp_b200.rank_sweep(model, shard[:250_001].contiguous().to(dev), rel.to(dev), triples.to(dev), ent_offset=offset,
+                            h_rows=h_rows.to(dev), t_rows=t_rows.to(dev))
+    c = blp_b200.rank_sweep(model, shard[250_001:].contiguous().to(dev), rel.to(dev), triples.to(dev),
+                            ent_offset=offset + 250_001, h_rows=h_rows.to(dev), t_rows=t_rows.to(dev))
+    assert torch.equal(a["gt"] + c["gt"], out["gt"]) and torch.equal(a["ge"] + c["ge"], out["ge"])
+
+
+@pytest.mark.parametrize("model,loss", [("transe", "margin"), ("distmult", "nll")])
+def test_train_wikidata5m_batch(model, loss, cuda_device):
+    """B = 1024 positives x K = 512 in-batch negatives with the device sampler's strided indices."""
+    b, k, d, n_rel = 1024, 512, 128, 822
+    g = torch.Generator().manual_seed(31)
+    ent = torch.randn(b, 2, d, generator=g)
+    if model == "transe":
+        ent = torch.nn.functional.normalize(ent, dim=-1)
+    rel_w = (torch.rand(n_rel, d, generator=g) * 2 - 1) * (6.0 / (n_rel + d)) ** 0.5
+    rels = torch.randint(0, n_rel, (b, 1), generator=g)
+    neg = blp_b200.get_negative_sampling_indices(b, k, device=cuda_device, seed=77)
+    res = ops.train_loss(model, loss, ent.to(cuda_device), rel_w.to(cuda_device), rels.to(cuda_device), neg,
+                         want_grad=True)
+    co = c_oracle.train_loss(model, loss, ent.numpy(), rel_w[rels[:, 0]].numpy(), neg.cpu().numpy(), 0.0)
+    assert abs(res["loss"].item() - float(co["loss"])) <= 1e-5 * abs(float(co["loss"]))
+    ge = res["grad_ent"].cpu().numpy()
+    assert np.abs(ge - co["grad_ent"]).max() <= 2e-5 * np.abs(co["grad_ent"]).max()
+    assert not ops.index_error_flag(res)
+
+
+def test_degenerate_shapes(cuda_device):
+    dev = cuda_device
+    ent, rel = torch.randn(50, 128, device=dev), torch.randn(3, 128, device=dev)
+    empty = torch.empty((0, 3), dtype=torch.int64, device=dev)
+    out = blp_b200.rank_sweep("distmult", ent, rel, empty)
+    assert out["gt"].shape == (2, 0) and out["sums"].tolist() == [0.0, 0.0, 0.0, 0.0]
+    didx = blp_b200.DeviceFilterIndex(np.array([[1, 2, 0]]), None, 50, 3, dev)
+    out = blp_b200.rank_sweep("distmult", ent, rel, empty, filter_index=didx)
+    assert out["gt_f"].shape == (2, 0)
+    neg = blp_b200.get_negative_sampling_indices(4, 0, device=dev)
+    assert tuple(neg.shape) == (4, 0, 2)
+    one = torch.tensor([[3, 3, 1]], device=dev)                          # head == tail, single triple
+    out = blp_b200.rank_sweep("simple", ent, rel, one)
+    assert out["gt"].shape == (2, 1) and bool((out["gt"] < out["ge"]).all())

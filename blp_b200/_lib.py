@@ -46,6 +46,7 @@ SYMBOLS = {
                                   _vp, _vp, _vp, _vp, _vp, _vp]),
     "blp_mrr_breakdown": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "blp_negative_sample": (_i32, [_i64, _i64, _i64, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
+    "blp_store_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i64, _vp]),
     "blp_profile_events": (_i32, [_i32, _vp, _vp]),
     "blp_pipe_probe": (_i32, [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }

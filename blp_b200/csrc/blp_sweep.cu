@@ -209,7 +209,12 @@ __host__ __device__ __forceinline__ constexpr bool pair_is_head(int q) {
 // qv = this warp's first query pair.  On return s[q][i] holds the final bilinear scores of queries 2q, 2q+1,
 // or the L1 distance (the caller flips the sign) for TransE.  Loop nests are ordered (pair, position,
 // candidate) so consecutive packed instructions belong to different accumulation chains.
-template <int MODEL, int ROLE, int TQP, int TC>
+//
+// SHARED_R (TransE, mixed role): the thread's TQP head-prediction queries belong to triples with the SAME
+// relation (test triples sorted by relation), so w = fl(e + r) -- the first rounding of models.py:223 when the
+// candidate plays `heads` -- is computed once per (candidate, position) as a scalar and reused by every head
+// pair: 1 lane-op instead of 2 per pair.  Per query the operations and their order are unchanged (same bits).
+template <int MODEL, int ROLE, int TQP, int TC, bool SHARED_R = false>
 __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float *__restrict__ qv, f2 nz,
                                            f2 (&s)[TQP][TC]) {
 #define HEAD_PRED (pair_is_head<ROLE, TQP>(q))
@@ -220,9 +225,12 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
 
     if (MODEL == BLP_MODEL_TRANSE) {
         // strictly sequential L1 accumulation, natural order
+        // the kernel holds two copies of this loop nest (shared / per-query relation); the shared one is unrolled
+        // less so that the hot loop bodies stay inside the instruction cache (ncu: stall_no_instructions)
+        constexpr int kUnrollCC = SHARED_R ? 4 : 8;
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
+#pragma unroll kUnrollCC
         for (int cc = 0; cc < 8; ++cc) {
             const int c4 = cb * 8 + cc;
             float e[TC][4];
@@ -231,8 +239,31 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
                 const float4 v = tv.load(i, c4);
                 e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
             }
+            constexpr int kHeadPairs = (SHARED_R && ROLE == kRoleMixed) ? TQP / 2 : 0;
+            if (kHeadPairs > 0) {
+                // shared relation: r is the same in both halves of every head pair; take it from pair 0
+                const Q4 r4 = ldq4(qv, 0, 0, 4 * c4);
+                const f2 rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                f2 tv4[kHeadPairs > 0 ? kHeadPairs : 1][4];
 #pragma unroll
-            for (int q = 0; q < TQP; ++q) {
+                for (int q = 0; q < kHeadPairs; ++q) {
+                    const Q4 b = ldq4(qv, q, 1, 4 * c4);
+                    tv4[q][0] = b.x; tv4[q][1] = b.y; tv4[q][2] = b.z; tv4[q][3] = b.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float r_lo, r_hi;
+                    unpack2(rv[k], r_lo, r_hi);
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) {
+                        const f2 w = dup2(fadd(e[i][k], r_lo));
+#pragma unroll
+                        for (int q = 0; q < kHeadPairs; ++q) s[q][i] = add2(s[q][i], abs2(sub2(w, tv4[q][k])));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = kHeadPairs; q < TQP; ++q) {
                 const Q4 a = ldq4(qv, q, 0, 4 * c4);
                 const Q4 b = HEAD_PRED ? ldq4(qv, q, 1, 4 * c4) : q4_zero();
                 const f2 av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -486,6 +517,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         int cgt[C::SQ], cge[C::SQ];
 #pragma unroll
         for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
+        // TransE, mixed role: do this slot's head-prediction triples share one relation row?  (warp-uniform)
+        bool shared_r = false;
+        if (MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2) {
+            const long long tr0 = t0 + QM::triple(slot, 0);
+            shared_r = tr0 + C::TQP <= args.b;
+            if (shared_r) {
+                const float *r0 = args.r.row(tr0, kD);
+#pragma unroll
+                for (int q = 1; q < C::TQP; ++q) shared_r &= args.r.row(tr0 + q, kD) == r0;
+            }
+        }
 
         for (; id < seg_end; ++id, ++it) {
             const long long tile = id % ntiles;
@@ -496,7 +538,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
                 const TileView<MODEL> tv(&sm.ctile[buf][0], row_off);
-                if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
+                if (QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && shared_r)
+                    score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
+                else if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else score_tile<MODEL, kRoleTail, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
 #pragma unroll

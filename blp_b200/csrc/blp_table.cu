@@ -1,0 +1,65 @@
+// blp_table.cu -- entity-table production glue (a13, next row f4).
+//
+// The reference encodes the candidate entities in batches and copies each batch into one dense table on one
+// device: `batch_emb = model(...)` (which ends in F.normalize for TransE, models.py:38-43) followed by
+// `ent_emb[idx:idx + bs] = batch_emb` (train.py:95-123).  For an entity-sharded sweep every rank owns a row
+// block of the table, so the glue becomes: normalise the encoder's raw output rows and write the ones this
+// rank owns straight into its shard -- the full (N, D) table never exists on any single device.
+//
+// Arithmetic: F.normalize(x, dim=-1) = x / max(||x||_2, 1e-12) with ATen's CPU vector-norm order (8 lanes, one
+// accumulator per lane over consecutive 8-element blocks, separate mul / add roundings, lanes folded
+// sequentially from lane 0, scalar tail), IEEE sqrt and division -- bit-equal to the reference's CPU path
+// (oracle/np_oracle.py l2_normalize_rows, tests/golden/normalize.npz).
+#include "blp_common.cuh"
+
+namespace blp {
+
+constexpr int kStoreWarps = 8;
+
+// one warp per source row
+__global__ void __launch_bounds__(kStoreWarps * 32) store_rows_kernel(const float *__restrict__ emb, long long m, int d,
+                                                                      int normalize, const long long *__restrict__ dst_rows,
+                                                                      long long row0, float *__restrict__ shard,
+                                                                      long long n_local, long long ent_offset) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * kStoreWarps + warp;
+    if (i >= m) return;
+    const long long local = (dst_rows ? dst_rows[i] : row0 + i) - ent_offset;
+    if (local < 0 || local >= n_local) return;                   // another rank owns this row
+    const float *x = emb + i * d;
+    float *y = shard + local * d;
+    float denom = 1.0f;
+    if (normalize) {
+        const int full = d - d % 8;
+        float acc = 0.0f;
+        if (lane < 8)
+            for (int b = lane; b < full; b += 8) acc = fadd(acc, fmul(x[b], x[b]));
+        float s = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const float a = __shfl_sync(0xffffffffu, acc, l);
+            s = (l == 0) ? a : fadd(s, a);
+        }
+        for (int j = full; j < d; ++j) s = fadd(s, fmul(x[j], x[j]));
+        denom = fmaxf(__fsqrt_rn(s), 1e-12f);                    // norm.clamp_min(eps)
+    }
+    for (int j = lane; j < d; j += 32) y[j] = normalize ? __fdiv_rn(x[j], denom) : x[j];
+}
+
+}  // namespace blp
+
+using namespace blp;
+
+extern "C" int blp_store_rows(const float *emb, int64_t m, int d, int normalize, const int64_t *dst_rows, int64_t row0,
+                              float *ent_shard, int64_t n_local, int64_t ent_offset, void *stream) {
+    reset_launch_count();
+    if (m < 0 || d <= 0 || n_local < 0) { set_error("bad size argument"); return BLP_EINVAL; }
+    if (m == 0 || n_local == 0) return BLP_OK;
+    if (!emb || !ent_shard) { set_error("null pointer argument"); return BLP_EINVAL; }
+    const long long blocks = (m + kStoreWarps - 1) / kStoreWarps;
+    store_rows_kernel<<<(unsigned)blocks, kStoreWarps * 32, 0, (cudaStream_t)stream>>>(emb, m, d, normalize, (const long long *)dst_rows,
+                                                                                      row0, ent_shard, n_local, ent_offset);
+    count_launch();
+    BLP_CUDA(cudaGetLastError());
+    return BLP_OK;
+}

@@ -64,7 +64,7 @@ def gather_rows(ent_shard, ent_offset, idx, group=None):
 
 def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, filter_triples=None,
                filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384,
-               h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None):
+               h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None, sort_by_relation=True):
     """Rank every test triple against all candidate entities (train.py:128-171 for the whole sweep).
 
     rel_model   'transe' | 'distmult' | 'complex' | 'simple'
@@ -84,6 +84,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 (blp_rank_sweep_fast) -- scores within ~1e-6 * sum|terms|, ranks may differ for candidates
                 inside that band around the true score; `fast_table` = ops.fast_table(ent_emb) to reuse
                 the split table across calls
+    sort_by_relation   TransE exact mode: process the triples in relation order (one stable argsort per sweep; the
+                outputs come back in the caller's order).  Triples that share a relation let the kernel compute
+                fl(candidate + r) once for several head-prediction queries (~13 % fewer FP32 lane-ops); results are
+                bit-identical either way
     count_fn    test seam: replaces ops.eval_rank (same signature) so the sharding / collective logic can
                 be exercised without a GPU
 
@@ -123,6 +127,15 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             t_rows = gather_rows(ent_emb, ent_offset, triples[:, 1], group)
         if mode not in ("exact", "fast"):
             raise ValueError(f"unknown mode {mode!r}")
+        perm = None
+        if sort_by_relation and rel_model == "transe" and mode == "exact" and T > 32 and filter_csr is None:
+            perm = torch.argsort(triples[:, 2], stable=True)
+            triples = triples.index_select(0, perm)
+            if h_rows is not None:
+                h_rows, t_rows = h_rows.index_select(0, perm), t_rows.index_select(0, perm)
+            if filter_triples is not None and dev_index is None:
+                ft = filter_triples.cpu().numpy() if torch.is_tensor(filter_triples) else np.asarray(filter_triples)
+                filter_triples = ft.reshape(-1, 3)[perm.cpu().numpy()]
         if mode == "fast" and fast_table is None:
             fast_table = ops.fast_table(ent_emb)
             launches += 1
@@ -144,6 +157,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                                                dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
                                                None if h_rows is None else h_rows[lo:hi],
                                                None if t_rows is None else t_rows[lo:hi], ent_offset)
+        if perm is not None:
+            # back to the caller's order: slot perm[j] receives what was computed for sorted position j
+            buf = torch.empty_like(buf).index_copy_(2, perm, buf)
+            counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
     else:
         # test seam: the sharding / collective logic with a CPU stand-in for blp_eval_rank
         heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
@@ -178,6 +195,108 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             out["recip" + suffix], out["hits" + suffix], out["sums" + suffix] = recip, hits, sums
             out["launches"] += 1
     return out
+
+
+class RankSweepPlan:
+    """`rank_sweep` for repeated calls on the same table with a fixed number of test triples.
+
+    Everything that does not depend on the triples is done once: argument validation, output / scratch
+    allocation, the ctypes argument lists.  A call is then two or three C-ABI launches (blp_rank_sweep[_fast],
+    blp_filter_correct, blp_rank_metrics) and ~15 us of host time instead of ~65 us, which matters for the
+    reference's small eval batches (64 triples, train.py:128) and for the tensor-core mode, whose GPU time per
+    batch is of the same order.  The returned tensors are STATIC: the next call overwrites them.
+
+        plan = blp_b200.RankSweepPlan("distmult", ent_emb, model.rel_emb.weight, num_triples=64, mode="fast")
+        for triples in loader: out = plan(rows)      # out["sums"], out["gt"], ... as rank_sweep
+    """
+
+    def __init__(self, rel_model, ent_emb, rel_weight, num_triples, *, mode="exact", filter_index=None,
+                 k_values=K_VALUES, ent_offset=0, group=None, fast_table=None):
+        lib = ops.lib()
+        self.model_id = ops.model_id(rel_model)
+        dev = ops._require_cuda(ent_emb, rel_weight)
+        if ent_emb.dtype != torch.float32 or not ent_emb.is_contiguous() or ent_emb.dim() != 2:
+            raise ValueError("ent_emb must be a contiguous fp32 (N, D) tensor")
+        if mode not in ("exact", "fast"):
+            raise ValueError(f"unknown mode {mode!r}")
+        if filter_index is not None and not hasattr(filter_index, "workspace"):
+            raise ValueError("RankSweepPlan takes a utils.DeviceFilterIndex (built once per evaluation)")
+        self.ent, self.rel = ent_emb, ops._f32c(rel_weight.detach())
+        self.dev, self.T, self.mode, self.group = dev, int(num_triples), mode, group
+        self.world, _ = _world(group)
+        self.ent_offset = int(ent_offset)
+        n, d = ent_emb.shape
+        T = self.T
+        self.filtered = filter_index is not None
+        self.filter_index = filter_index
+        names = ("gt", "ge", "gt_f", "ge_f") if self.filtered else ("gt", "ge")
+        with ops._guard(dev):
+            ops._enter(dev)
+            buf = torch.empty((len(names) + 1, 2, T), dtype=torch.int32, device=dev)
+            self.counters = buf[:len(names)]
+            self.out = {name: buf[i] for i, name in enumerate(names)}
+            self.out["true_score"] = buf[len(names)].view(torch.float32)
+            ks, self._karr = ops._kvalues(k_values)
+            self._nk = len(ks)
+            for suffix in ("", "_f") if self.filtered else ("",):
+                self.out["recip" + suffix] = torch.empty((2 * T, 1), dtype=torch.float32, device=dev)
+                self.out["hits" + suffix] = torch.empty((2 * T, len(ks)), dtype=torch.uint8, device=dev)
+                self.out["sums" + suffix] = torch.empty(1 + len(ks), dtype=torch.float64, device=dev)
+            self.fast_table = None
+            self._qws = None
+            if mode == "fast":
+                self.fast_table = fast_table if fast_table is not None else ops.fast_table(ent_emb)
+                self._qws = torch.empty(int(lib.blp_fast_query_bytes(T)), dtype=torch.uint8, device=dev)
+        p = ops._ptr
+        o = self.out
+        # blp_rank_sweep(model, ent, n, off, d, rel, R, TRIPLES, t, H_ROWS, T_ROWS, indptr, idx, tail_off, gt, ge, gt_f, ge_f, ts, ...)
+        self._head = (self.model_id, p(ent_emb), n, self.ent_offset, d, p(self.rel), self.rel.shape[0])
+        self._tail = (None, None, T, p(o["gt"]), p(o["ge"]), None, None, p(o["true_score"]))
+        if mode == "fast":
+            self._tail = self._tail + (p(self.fast_table), p(self._qws), None, n)
+        self._sweep_fn = lib.blp_rank_sweep_fast if mode == "fast" else lib.blp_rank_sweep
+        self._lib = lib
+        for suffix in ("", "_f") if self.filtered else ("",):
+            o["hits" + suffix + "_bool"] = o["hits" + suffix].view(torch.bool)
+        self.launches = 0
+
+    def __call__(self, triples, h_rows=None, t_rows=None):
+        T, o, lib = self.T, self.out, self._lib
+        if (triples.shape != (T, 3) or triples.dtype != torch.int64 or not triples.is_contiguous()
+                or triples.device != self.dev):
+            raise ValueError(f"triples must be a contiguous int64 ({T}, 3) tensor on {self.dev}")
+        if self.world > 1 and h_rows is None:
+            h_rows = gather_rows(self.ent, self.ent_offset, triples[:, 0], self.group)
+            t_rows = gather_rows(self.ent, self.ent_offset, triples[:, 1], self.group)
+        if h_rows is not None:
+            h_rows, t_rows = ops._f32c(h_rows), ops._f32c(t_rows)
+        with ops._guard(self.dev):
+            _, stream = ops._enter(self.dev)
+            if T > 0:
+                ops.check(self._sweep_fn(*self._head, triples.data_ptr(), T, ops._ptr(h_rows), ops._ptr(t_rows),
+                                         *self._tail, stream), "blp_rank_sweep")
+                launches = ops._lib.last_launch_count()
+                if self.filtered:
+                    fi = self.filter_index
+                    ops.check(lib.blp_filter_correct(*self._head, triples.data_ptr(), T, ops._ptr(h_rows), ops._ptr(t_rows),
+                                                     ops._ptr(fi.workspace), fi.num_edges, fi.num_rows, T,
+                                                     ops._ptr(o["true_score"]), ops._ptr(o["gt"]), ops._ptr(o["ge"]),
+                                                     ops._ptr(o["gt_f"]), ops._ptr(o["ge_f"]), stream), "blp_filter_correct")
+                    launches += 1
+            else:
+                launches = 0
+            if self.world > 1:
+                _dist().all_reduce(self.counters, group=self.group)
+            for suffix in ("", "_f") if self.filtered else ("",):
+                ops.check(lib.blp_rank_metrics(ops._ptr(o["gt" + suffix]), ops._ptr(o["ge" + suffix]), 2 * T, self._karr,
+                                               self._nk, ops._ptr(o["recip" + suffix]), ops._ptr(o["hits" + suffix]),
+                                               ops._ptr(o["sums" + suffix]), stream), "blp_rank_metrics")
+                launches += 1
+        res = dict(o)
+        for suffix in ("", "_f") if self.filtered else ("",):
+            res["hits" + suffix] = res.pop("hits" + suffix + "_bool")
+        res["launches"] = launches
+        return res
 
 
 def breakdowns(out, triples_ids, new_entities=None, rel_categories=None, max_ent_id=None):

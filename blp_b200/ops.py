@@ -406,6 +406,28 @@ def negative_sample(batch_size, num_negatives, repeats=1, *, device, seed=0, off
     return storage.transpose(0, 1)
 
 
+# ------------------------------------------------- entity-table production ----
+def store_rows(ent_shard, emb, rows=None, row0=0, normalize=False, ent_offset=0):
+    """`ent_emb[idx:idx + bs] = F.normalize(batch_emb)` (models.py:38-43, train.py:95-123) into a row shard.
+
+    ent_shard (N_local, D) fp32 contiguous: this rank's rows [ent_offset, ent_offset + N_local) of the table;
+    emb (m, D): raw encoder outputs; rows: optional int64 (m,) global destination rows (default row0 + i).
+    Rows owned by other ranks are skipped.  Returns ent_shard."""
+    dev = _require_cuda(ent_shard, emb, rows)
+    if ent_shard.dtype != torch.float32 or not ent_shard.is_contiguous() or ent_shard.dim() != 2:
+        raise ValueError("ent_shard must be a contiguous fp32 (N_local, D) tensor")
+    emb = _f32c(emb.detach()).reshape(-1, ent_shard.shape[1])
+    if rows is not None:
+        rows = rows.to(torch.int64).reshape(-1).contiguous()
+        if rows.numel() != emb.shape[0]:
+            raise ValueError("rows must have one entry per row of emb")
+    with _guard(dev):
+        _, stream = _enter(dev)
+        check(lib().blp_store_rows(_ptr(emb), emb.shape[0], emb.shape[1], int(bool(normalize)), _ptr(rows), int(row0),
+                                   _ptr(ent_shard), ent_shard.shape[0], int(ent_offset), stream), "blp_store_rows")
+    return ent_shard
+
+
 # ------------------------------------------------------ fused compute_loss ----
 _ws_lock = threading.Lock()
 _workspaces = {}

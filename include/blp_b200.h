@@ -246,6 +246,15 @@ int blp_mrr_breakdown(const float *recip, int64_t t, int64_t tail_off, const int
 int blp_negative_sample(int64_t batch, int64_t num_neg, int64_t repeats, uint64_t seed, uint64_t offset,
                         int64_t *out, void *stream);
 
+/* ---- a13 / next row f4  entity-table production: F.normalize + scatter into a row shard ---------
+ * Replaces `F.normalize(ent_emb, dim=-1)` (models.py:38-43, TransE only) and
+ * `ent_emb[idx:idx + bs] = batch_emb` (train.py:95-123) for a row-sharded table: source row i of
+ * emb [m, d] goes to global row dst_rows[i] (or row0 + i when dst_rows is NULL); rows outside
+ * [ent_offset, ent_offset + n_local) are skipped, so every rank can be handed the same encoder batch
+ * and keeps only what it owns.  normalize != 0: x / max(||x||_2, 1e-12) in ATen's CPU order (bit-equal). */
+int blp_store_rows(const float *emb, int64_t m, int d, int normalize, const int64_t *dst_rows, int64_t row0,
+                   float *ent_shard, int64_t n_local, int64_t ent_offset, void *stream);
+
 /* ---- measurement aid ------------------------------------------------------
  * FP32 pipe micro-benchmarks used by bench.py to measure the lane-op rate the
  * ALU-bound exact sweeps are compared against ("measure

@@ -317,8 +317,31 @@ def check_sum_orders():
     print("orders ok: oracle sum / L1 orders are bit-equal to torch", torch.__version__)
 
 
+def gen_normalize():
+    """models.py:38-43: LinkPrediction.encode -> F.normalize for TransE, through the reference's own class."""
+    out = {}
+    for d in (128, 300, 768, 100):
+        torch.manual_seed(60 + d)
+        m = ref_models.TransductiveLinkPrediction(d, "transe", "margin", 40, 3, 0)
+        torch.nn.init.normal_(m.ent_emb.weight, std=0.7)
+        with torch.no_grad():
+            m.ent_emb.weight[3] = 0.0                      # zero row: clamp_min(eps) path
+            m.ent_emb.weight[5] *= 1e-20                   # tiny norm
+        ents = torch.arange(40)
+        y = m.encode(ents).detach()
+        x = m.ent_emb.weight.detach()
+        assert_bits(f"normalize d={d}", y.numpy(), np_oracle.l2_normalize_rows(x.numpy()))
+        out[f"x_{d}"] = x.numpy()
+        out[f"y_{d}"] = y.numpy()
+    np.savez_compressed(os.path.join(OUT, "normalize.npz"), **out)
+    print("normalize ok: oracle l2_normalize_rows is bit-equal to the reference's encode()")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--normalize-only" in sys.argv:
+        gen_normalize()
+        return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     check_sum_orders()
     gen_kat()
@@ -334,6 +357,7 @@ def main():
         gen_train(model, "nll", b=6, k=10, d=128, regularizer=1e-2 if model == "transe" else 0.0, seed=40 + i)
     for i, model in enumerate(("transe", "distmult", "complex", "simple")):
         gen_eval_loop(model, seed=50 + i)
+    gen_normalize()
     print("golden vectors written to", OUT)
 
 

@@ -67,6 +67,26 @@ def seq_sum_lastdim(x):
     return s
 
 
+def l2_normalize_rows(x, eps=1e-12):
+    """F.normalize(x, dim=-1) (models.py:40-41) with ATen's CPU vector-norm order: 8 lanes, one accumulator per
+    lane over consecutive 8-element blocks (separate mul / add roundings, no FMA), lanes folded sequentially from
+    lane 0, then the scalar tail; sqrt; x / max(norm, eps).  Verified bit-equal to torch 2.11 CPU (gen_golden.py)."""
+    x = np.asarray(x, f32)
+    d = x.shape[-1]
+    full = d - d % 8
+    acc = np.zeros(x.shape[:-1] + (8,), f32)
+    for b in range(0, full, 8):
+        blk = x[..., b:b + 8]
+        acc = acc + blk * blk
+    s = acc[..., 0].copy()
+    for lane in range(1, 8):
+        s = s + acc[..., lane]
+    for j in range(full, d):
+        s = s + x[..., j] * x[..., j]
+    norm = np.sqrt(s).astype(f32)
+    return (x / np.maximum(norm, f32(eps))[..., None]).astype(f32)
+
+
 def transe_score(heads, tails, rels):
     """models.py:222-223."""
     heads, tails, rels = (np.asarray(a, f32) for a in (heads, tails, rels))

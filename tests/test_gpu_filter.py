@@ -173,3 +173,59 @@ def test_negative_sampler_feeds_compute_loss_in_place(cuda_device):
     assert np.abs(ent_embs.grad.cpu().numpy() - co["grad_ent"]).max() <= 2e-5 * np.abs(co["grad_ent"]).max()
     with pytest.raises(ValueError):
         blp_b200.get_negative_sampling_indices(1, 4, device=cuda_device)            # data.py:289-291 needs batch > 1
+
+
+@pytest.mark.parametrize("model,mode", [("transe", "exact"), ("complex", "exact"), ("distmult", "fast")])
+def test_rank_sweep_plan_equals_rank_sweep(model, mode, cuda_device):
+    """RankSweepPlan = rank_sweep with the per-call host work hoisted: same integers, same metrics, for fresh
+    triples on every call, raw and filtered."""
+    g = golden("eval_loop_" + ("distmult" if model == "distmult" else model))
+    ent2idx = blp_b200.make_ent2idx(torch.from_numpy(g["entities"]), int(g["n_ids"]) - 1)
+    triples = torch.from_numpy(g["triples"])
+    rows = torch.stack([ent2idx[triples[:, 0]], ent2idx[triples[:, 1]], triples[:, 2]], dim=1).to(cuda_device)
+    ent, rel = _t(g["ent_emb"], cuda_device), _t(g["rel_weight"], cuda_device)
+    didx = blp_b200.DeviceFilterIndex(g["graph_edges"], ent2idx, ent.shape[0], rel.shape[0], cuda_device)
+    T = 32
+    plan = blp_b200.RankSweepPlan(model, ent, rel, T, mode=mode, filter_index=didx)
+    for lo in (0, 32, 64):
+        chunk = rows[lo:lo + T].contiguous()
+        got = plan(chunk)
+        want = blp_b200.rank_sweep(model, ent, rel, chunk, filter_index=didx, mode=mode)
+        for k in ("gt", "ge", "gt_f", "ge_f", "true_score", "recip", "recip_f", "hits", "hits_f", "sums", "sums_f"):
+            assert torch.equal(got[k], want[k]), (k, lo)
+    with pytest.raises(ValueError):
+        plan(rows[:T + 1].contiguous())
+
+
+# ------------------------------------------------------- entity-table production (row f4) ----
+@pytest.mark.parametrize("d", (128, 300, 768, 100))
+def test_store_rows_normalize_matches_reference_encode(d, cuda_device):
+    """blp_store_rows(normalize=1) == the reference's encode() bits (golden normalize.npz), incl. zero / tiny rows."""
+    g = golden("normalize")
+    x, y = g[f"x_{d}"], g[f"y_{d}"]
+    shard = torch.full((x.shape[0], d), float("nan"), device=cuda_device)
+    blp_b200.store_rows(shard, _t(x, cuda_device), normalize=True)
+    assert np.array_equal(shard.cpu().numpy(), y)
+
+
+def test_store_rows_scatters_into_row_shards(cuda_device):
+    """train.py:95-123 with the table row-sharded: every rank is handed every encoder batch and keeps its rows;
+    the union of the shards is the reference's dense table, and the sweep over the shards equals the dense sweep."""
+    from oracle import np_oracle
+    n, d, world, bs = 1000, 128, 3, 96
+    g = torch.Generator().manual_seed(4)
+    raw = torch.randn(n, d, generator=g)
+    dense = torch.from_numpy(np_oracle.l2_normalize_rows(raw.numpy()))                 # == F.normalize(raw)
+    shards = []
+    for rank in range(world):
+        lo, hi = blp_b200.shard_bounds(n, world, rank)
+        shard = torch.zeros((hi - lo, d), device=cuda_device)
+        for idx in range(0, n, bs):                                                     # the reference's encode loop
+            blp_b200.store_rows(shard, raw[idx:idx + bs].to(cuda_device), row0=idx, normalize=True, ent_offset=lo)
+        shards.append(shard)
+    assert torch.equal(torch.cat(shards).cpu(), dense)
+    # permuted destinations (entities[idx] order) and no normalisation (bilinear models, models.py:18)
+    perm = torch.randperm(n, generator=g)
+    full = torch.zeros((n, d), device=cuda_device)
+    blp_b200.store_rows(full, raw.to(cuda_device), rows=perm.to(cuda_device))
+    assert torch.equal(full.cpu()[perm], raw)

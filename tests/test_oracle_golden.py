@@ -97,3 +97,10 @@ def test_aten_sum_order_self_consistent():
         a = np_oracle.aten_sum_lastdim(x)
         b = np.array([c_oracle.aten_sum(v) for v in x])
         assert np.array_equal(a, b), L
+
+
+def test_np_oracle_normalize_bits():
+    """F.normalize through the reference's encode() (models.py:38-43): ATen vector-norm order, any width."""
+    g = golden("normalize")
+    for d in (128, 300, 768, 100):
+        assert np.array_equal(np_oracle.l2_normalize_rows(g[f"x_{d}"]), g[f"y_{d}"]), d

@@ -42,7 +42,10 @@ cases = {
     "GraphedLossStep(x, rels, neg) (3 D2D copies + replay)": lambda: step(x0, rels, neg),
     "rank_sweep (T=64, N=256)": lambda: blp_b200.rank_sweep("transe", ent, m.rel_emb.weight, rows),
     "ops.rank_metrics": None,
+    "RankSweepPlan (T=64, N=256)": None,
 }
+plan = blp_b200.RankSweepPlan("transe", ent, m.rel_emb.weight, T)
+cases["RankSweepPlan (T=64, N=256)"] = lambda: plan(rows)
 out = blp_b200.rank_sweep("transe", ent, m.rel_emb.weight, rows)
 cases["ops.rank_metrics"] = lambda: ops.rank_metrics(out["gt"], out["ge"], (1, 3, 10))
 for name, fn in cases.items():

@@ -23,6 +23,8 @@ ent = ent.to(dev)
 rel = ((torch.rand(237, 128, generator=g) * 2 - 1) * 0.128).to(dev)
 triples = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g),
                        torch.randint(0, 237, (E,), generator=g)], dim=1).to(dev)
+if os.environ.get("SORT_REL"):
+    triples = triples[torch.argsort(triples[:, 2], stable=True)].contiguous()
 out = {k: torch.empty((2, E), dtype=torch.int32, device=dev) for k in ("gt", "ge")}
 out["true_score"] = torch.empty((2, E), dtype=torch.float32, device=dev)
 ws = ops.fast_table(ent) if mode == "fast" else None

@@ -46,6 +46,79 @@ __global__ void __launch_bounds__(kStoreWarps * 32) store_rows_kernel(const floa
     for (int j = lane; j < d; j += 32) y[j] = normalize ? __fdiv_rn(x[j], denom) : x[j];
 }
 
+// d % 4 == 0, d <= 256, 16-byte aligned rows: a warp takes FOUR rows at a time.  The rows move through registers
+// with coalesced 128-bit accesses (lane holds float4 number lane + 32 * u of each row, all loads in flight
+// together); the squares are parked in shared memory so that lane group g = lane / 8 can replay ATen's per-lane
+// accumulation order for row g (8 chains per row, 4 rows in parallel), the group's first lane order folds the 8
+// lane sums, and every lane divides what it holds.
+constexpr int kStoreRows = 4;
+template <int V4>
+__global__ void __launch_bounds__(kStoreWarps * 32) store_rows_vec_kernel(const float *__restrict__ emb, long long m, int d,
+                                                                          int normalize, const long long *__restrict__ dst_rows,
+                                                                          long long row0, float *__restrict__ shard,
+                                                                          long long n_local, long long ent_offset) {
+    extern __shared__ float sq_smem[];                               // [kStoreWarps][kStoreRows][d]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long first = ((long long)blockIdx.x * kStoreWarps + warp) * kStoreRows;
+    if (first >= m) return;
+    const int nv = d >> 2;
+    float4 v[kStoreRows][V4];
+    long long local[kStoreRows];
+#pragma unroll
+    for (int g = 0; g < kStoreRows; ++g) {
+        const long long i = first + g;
+        local[g] = -1;
+        if (i < m) {
+            local[g] = (dst_rows ? dst_rows[i] : row0 + i) - ent_offset;
+            if (local[g] >= n_local) local[g] = -1;
+        }
+        const float4 *x4 = reinterpret_cast<const float4 *>(emb + i * d);
+#pragma unroll
+        for (int u = 0; u < V4; ++u) {
+            v[g][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (local[g] >= 0 && lane + 32 * u < nv) v[g][u] = __ldg(x4 + lane + 32 * u);
+        }
+    }
+    float den[kStoreRows] = {1.f, 1.f, 1.f, 1.f};
+    if (normalize) {
+        float *sq = sq_smem + (size_t)warp * kStoreRows * d;
+#pragma unroll
+        for (int g = 0; g < kStoreRows; ++g)
+#pragma unroll
+            for (int u = 0; u < V4; ++u)
+                if (lane + 32 * u < nv)
+                    reinterpret_cast<float4 *>(sq + g * d)[lane + 32 * u] =
+                        make_float4(fmul(v[g][u].x, v[g][u].x), fmul(v[g][u].y, v[g][u].y), fmul(v[g][u].z, v[g][u].z),
+                                    fmul(v[g][u].w, v[g][u].w));
+        __syncwarp();
+        const int grp = lane >> 3, l = lane & 7;
+        const float *row = sq + grp * d;
+        const int full = d - d % 8;
+        float acc = 0.0f;
+        for (int b = l; b < full; b += 8) acc = fadd(acc, row[b]);
+        float s = __shfl_sync(0xffffffffu, acc, grp * 8);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) s = fadd(s, __shfl_sync(0xffffffffu, acc, grp * 8 + j));
+        for (int j = full; j < d; ++j) s = fadd(s, row[j]);
+        const float mine = fmaxf(__fsqrt_rn(s), 1e-12f);
+#pragma unroll
+        for (int g = 0; g < kStoreRows; ++g) den[g] = __shfl_sync(0xffffffffu, mine, g * 8);
+    }
+#pragma unroll
+    for (int g = 0; g < kStoreRows; ++g) {
+        if (local[g] < 0) continue;
+        float4 *y4 = reinterpret_cast<float4 *>(shard + local[g] * d);
+#pragma unroll
+        for (int u = 0; u < V4; ++u)
+            if (lane + 32 * u < nv) {
+                float4 o = v[g][u];
+                if (normalize)
+                    o = make_float4(__fdiv_rn(o.x, den[g]), __fdiv_rn(o.y, den[g]), __fdiv_rn(o.z, den[g]), __fdiv_rn(o.w, den[g]));
+                y4[lane + 32 * u] = o;
+            }
+    }
+}
+
 }  // namespace blp
 
 using namespace blp;
@@ -57,8 +130,21 @@ extern "C" int blp_store_rows(const float *emb, int64_t m, int d, int normalize,
     if (m == 0 || n_local == 0) return BLP_OK;
     if (!emb || !ent_shard) { set_error("null pointer argument"); return BLP_EINVAL; }
     const long long blocks = (m + kStoreWarps - 1) / kStoreWarps;
-    store_rows_kernel<<<(unsigned)blocks, kStoreWarps * 32, 0, (cudaStream_t)stream>>>(emb, m, d, normalize, (const long long *)dst_rows,
-                                                                                      row0, ent_shard, n_local, ent_offset);
+    const bool vec = (d % 4 == 0) && d <= 256 &&
+                     ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(ent_shard)) & 15u) == 0;
+    if (vec) {
+        const size_t smem = normalize ? (size_t)kStoreWarps * kStoreRows * d * sizeof(float) : 0;
+        const long long vblocks = (m + kStoreWarps * kStoreRows - 1) / (kStoreWarps * kStoreRows);
+        if (d <= 128)
+            store_rows_vec_kernel<1><<<(unsigned)vblocks, kStoreWarps * 32, smem, (cudaStream_t)stream>>>(
+                emb, m, d, normalize, (const long long *)dst_rows, row0, ent_shard, n_local, ent_offset);
+        else
+            store_rows_vec_kernel<2><<<(unsigned)vblocks, kStoreWarps * 32, smem, (cudaStream_t)stream>>>(
+                emb, m, d, normalize, (const long long *)dst_rows, row0, ent_shard, n_local, ent_offset);
+    } else {
+        store_rows_kernel<<<(unsigned)blocks, kStoreWarps * 32, 0, (cudaStream_t)stream>>>(
+            emb, m, d, normalize, (const long long *)dst_rows, row0, ent_shard, n_local, ent_offset);
+    }
     count_launch();
     BLP_CUDA(cudaGetLastError());
     return BLP_OK;

@@ -87,3 +87,54 @@ def eval_batch(model, ent_emb, heads, tails, rel_rows, k_values, filter_mask=Non
         pred[filter_mask] = pred.min() - 1.0
         out["recip_f"], out["hits_f"] = rank_metrics(pred, true, k_values)
     return out
+
+
+# ---- CPU restatements of the rows either side of the hot path (timing baselines for SURVEY section 8f) ----
+def sample_negative_indices(batch_size, num_negatives, repeats=1):   # data.py:35-81
+    """In-batch corruption indices the way the reference draws them: a (B, 2B) weight matrix that is zero on the
+    own pair, torch.multinomial with replacement, a coin per negative for the corrupted side; returns the
+    transposed (B * repeats, K, 2) view."""
+    n = 2 * batch_size
+    own = torch.arange(n).view(batch_size, 2)
+    weights = torch.ones(batch_size, n)
+    weights.scatter_(1, own, torch.zeros(batch_size, 2))
+    draws = weights.multinomial(num_negatives * repeats, replacement=True).t().reshape(-1)
+    total = batch_size * num_negatives * repeats
+    side = torch.randint(0, 2, [total])
+    out = own.repeat((num_negatives * repeats, 1))
+    out[torch.arange(total), side] = draws
+    return out.view(-1, batch_size * repeats, 2).transpose(0, 1)
+
+
+def triple_filter_masks(triples, out_edges, in_edges, num_ents, ent2idx):   # utils.py:46-83
+    """Dense (B, N) bool masks of known tails / heads per test triple, built with the reference's per-edge Python loops.
+    out_edges[h] / in_edges[t] list the (head, tail, rel) edges of the filtering graph (what graph.out_edges /
+    graph.in_edges iterate)."""
+    b = triples.shape[0]
+    heads_mask = torch.zeros((b, num_ents), dtype=torch.bool)
+    tails_mask = torch.zeros((b, num_ents), dtype=torch.bool)
+    for i, (head, tail, rel) in enumerate(triples.tolist()):
+        for (_, t, r) in out_edges.get(head, ()):
+            if r == rel and t != tail and ent2idx[t] != -1:
+                tails_mask[i, ent2idx[t]] = True
+        for (h, _, r) in in_edges.get(tail, ()):
+            if r == rel and h != head and ent2idx[h] != -1:
+                heads_mask[i, ent2idx[h]] = True
+    return heads_mask, tails_mask
+
+
+def mrr_by_new_position(triples, recip, new_entities):   # utils.py:114-147
+    sums, counts = torch.zeros(3), torch.zeros(3)
+    n = triples.shape[0]
+    for i, (h, t, _) in enumerate(triples):
+        head, tail = h.item(), t.item()
+        v = (recip[i] + recip[i + n]).item() / 2.0
+        slot = 0 if (head in new_entities and tail in new_entities) else 1 if head in new_entities else 2 if tail in new_entities else None
+        if slot is not None:
+            sums[slot] += v
+            counts[slot] += 1.0
+    return sums, counts
+
+
+def normalize_rows(x):   # models.py:40-41
+    return F.normalize(x, dim=-1)

@@ -208,6 +208,16 @@ def test_store_rows_normalize_matches_reference_encode(d, cuda_device):
     assert np.array_equal(shard.cpu().numpy(), y)
 
 
+@pytest.mark.parametrize("d", (67, 1030, 2048))
+def test_store_rows_normalize_other_widths(d, cuda_device):
+    """Widths outside the vectorised path (odd d, d > 1024) against the oracle restatement of F.normalize."""
+    from oracle import np_oracle
+    x = torch.randn(33, d, generator=torch.Generator().manual_seed(d))
+    shard = torch.empty((33, d), device=cuda_device)
+    blp_b200.store_rows(shard, x.to(cuda_device), normalize=True)
+    assert np.array_equal(shard.cpu().numpy(), np_oracle.l2_normalize_rows(x.numpy()))
+
+
 def test_store_rows_scatters_into_row_shards(cuda_device):
     """train.py:95-123 with the table row-sharded: every rank is handed every encoder batch and keeps its rows;
     the union of the shards is the reference's dense table, and the sweep over the shards equals the dense sweep."""

@@ -19,6 +19,8 @@
 // The working set (2B rows, the int64 index tensor) is L2 resident; at B=64 the
 // whole step is launch-latency bound, which is why it is a single launch plus
 // one memset.  The scalar loss is reduced deterministically by the last CTA.
+#include <stdlib.h>
+
 #include "blp_common.cuh"
 
 namespace blp {
@@ -215,22 +217,31 @@ __global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a)
     const long long ke = min(a.k, kb + kps);
     const long long *nrow = a.neg_idx + b * a.s0;
 
-    for (long long k0 = kb + (long long)warp * ILP; k0 < ke; k0 += (long long)kTrainWarps * ILP) {
+    // every warp owns a contiguous run of this slice's negatives; it fetches the index pairs of 32 negatives with one
+    // load per lane (the indices of one row are 2B * 8 bytes apart in the reference sampler's layout, data.py:77-79)
+    // and hands them out by shuffle, so the dependent index -> row load chain is paid once per 32 negatives
+    const long long per_warp = (ke - kb + kTrainWarps - 1) / kTrainWarps;
+    const long long wb = kb + (long long)warp * per_warp, we = min(ke, wb + per_warp);
+    for (long long base = wb; base < we; base += 32) {
+    long long li0 = 2 * b, li1 = 2 * b + 1;
+    if (base + lane < we) {
+        li0 = nrow[(base + lane) * a.s1];
+        li1 = nrow[(base + lane) * a.s1 + a.s2];
+        if (li0 < 0 || li0 >= nb2 || li1 < 0 || li1 >= nb2) {
+            *a.err_flag = 1;
+            li0 = 2 * b; li1 = 2 * b + 1;
+        }
+    }
+    const int cnt = (int)min(32ll, we - base);
+    for (int u0 = 0; u0 < cnt; u0 += ILP) {
+        const long long k0 = base + u0;
         long long i0[ILP], i1[ILP];
         Row<NCH2> nh[ILP], nt[ILP];
         float part[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-            const long long kk = k0 + u;
-            i0[u] = 0; i1[u] = 0;
-            if (kk < ke) {
-                i0[u] = nrow[kk * a.s1];
-                i1[u] = nrow[kk * a.s1 + a.s2];
-                if (i0[u] < 0 || i0[u] >= nb2 || i1[u] < 0 || i1[u] >= nb2) {
-                    if (lane == 0) *a.err_flag = 1;
-                    i0[u] = 2 * b; i1[u] = 2 * b + 1;
-                }
-            }
+            i0[u] = __shfl_sync(0xffffffffu, li0, (u0 + u) & 31);
+            i1[u] = __shfl_sync(0xffffffffu, li1, (u0 + u) & 31);
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a)
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
             const long long kk = k0 + u;
-            if (kk >= ke) continue;   // warp-uniform
+            if (kk >= we) continue;   // warp-uniform
             const float sc = finish_score<MODEL>(part[u]);
             if (a.neg_scores && lane == 0) a.neg_scores[b * a.k + kk] = sc;
             float w;
@@ -290,6 +301,7 @@ __global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a)
                 }
             }
         }
+    }
     }
 
     // positive-side gradient: margin d/dpos = -sum_k w_bk (each warp adds its share); nll: -sigmoid(-pos)/(2B)
@@ -436,8 +448,14 @@ extern "C" int blp_train_loss(int model, int loss, const float *ent_embs, const 
     a.err_flag = reinterpret_cast<int *>(workspace) + 1;
     a.partials = reinterpret_cast<float *>(workspace) + 16;
     // enough CTAs to cover the SMs about twice, at least one 16-warp pass of negatives per CTA
+    // one wave of CTAs: every extra CTA repeats the positive-row prologue and the register-accumulator flush, and a
+    // second wave costs a full latency chain (B=64, K=512: 2 slices = 20.5 us, 8 slices = 30 us)
     int slices = 1;
-    while (slices < 8 && b * slices < 296 && k / (slices * 2) >= kTrainWarps * 2) slices *= 2;
+    while (slices < 8 && b * slices * 2 <= 160 && k / (slices * 2) >= 64) slices *= 2;
+    {
+        const char *e = getenv("BLP_TRAIN_SLICES");       // tuning aid
+        if (e && atoi(e) >= 1 && atoi(e) <= 8) slices = atoi(e);
+    }
     a.slices = slices;
     switch (model) {
     case BLP_MODEL_TRANSE: return dispatch_train<BLP_MODEL_TRANSE>(a, grad, st);

@@ -462,18 +462,41 @@ def main_b200(args):
     host_sums = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     landed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # host -> device prefetch, the way a pinned-memory DataLoader feeds a training loop: the inputs of step i + 1 cross
+    # PCIe on a copy stream into one of two device staging slots while step i computes; every step still moves its
+    # own h2d bytes inside the timed region
+    copy_stream = torch.cuda.Stream()
+    stage = [{"ent": torch.empty_like(h_ent_embs, device=dev), "rels": torch.empty_like(h_rels, device=dev),
+              "neg": torch.empty_like(h_neg, device=dev), "tr": torch.empty_like(h_triples[0], device=dev)} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_prefetch(i):
+        slot = stage[i & 1]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])            # the step that last used this slot has read it
+            slot["ent"].copy_(h_ent_embs, non_blocking=True)
+            slot["rels"].copy_(h_rels, non_blocking=True)
+            slot["neg"].copy_(h_neg, non_blocking=True)
+            slot["tr"].copy_(h_triples[i % len(h_triples)], non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
     def e2e_issue(i):
-        tr = h_triples[i % len(h_triples)].to(dev, non_blocking=True)
+        main = torch.cuda.current_stream()
+        if i == e2e_first[0]:
+            e2e_prefetch(i)
+        e2e_prefetch(i + 1)
+        main.wait_event(ready[i & 1])
+        slot = stage[i & 1]
         if graphed is not None:
-            loss, _ = graphed(h_ent_embs, h_rels, h_neg)          # H2D into the static buffers, then one graph launch
+            loss, _ = graphed(slot["ent"], slot["rels"], slot["neg"])   # into the graph's static buffers, one graph launch
         else:
-            x = h_ent_embs.to(dev, non_blocking=True).requires_grad_(True)
-            r_ = h_rels.to(dev, non_blocking=True)
-            ng = h_neg.to(dev, non_blocking=True).transpose(0, 1)
+            x = slot["ent"].clone().requires_grad_(True)
             rel_w.grad = None
-            loss = model.compute_loss(x, r_, ng)
+            loss = model.compute_loss(x, slot["rels"], slot["neg"].transpose(0, 1))
             loss.backward()
-        out = plan(tr)
+        out = plan(slot["tr"])
+        consumed[i & 1].record(main)
         # D2H: the loss scalar (train.py:352) + the 4 fp64 metric accumulators (train.py:154-157)
         host_loss[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
         host_sums[i & 1].copy_(out["sums"], non_blocking=True)
@@ -483,7 +506,10 @@ def main_b200(args):
         landed[i & 1].synchronize()
         return float(host_loss[i & 1][0]), {"mrr": float(host_sums[i & 1][0]) / (2 * e)}
 
+    e2e_first = [0]
+
     def e2e_step(i):
+        e2e_first[0] = i
         e2e_issue(i)
         return e2e_read(i)
 
@@ -493,6 +519,7 @@ def main_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = steps
     ev0.record()
+    e2e_first[0] = 0
     for i in range(e2e_steps):
         e2e_issue(i)
         if i > 0:

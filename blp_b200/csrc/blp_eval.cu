@@ -65,67 +65,7 @@ __global__ void __launch_bounds__(kTrue128Warps * 32) true_score128_kernel(const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i = (long long)blockIdx.x * kTrue128Warps + warp;
     if (i >= b) return;
-    const float *h = hr.row(i, kD), *t = tr.row(i, kD), *r = rr.row(i, kD);
-    float *tm = terms[warp];
-    constexpr int L = (MODEL == BLP_MODEL_COMPLEX || MODEL == BLP_MODEL_SIMPLE) ? kD / 2 : kD;
-    if (MODEL == BLP_MODEL_TRANSE || MODEL == BLP_MODEL_DISTMULT) {
-        const float4 hv = __ldg(reinterpret_cast<const float4 *>(h) + lane), tv = __ldg(reinterpret_cast<const float4 *>(t) + lane),
-                     rv = __ldg(reinterpret_cast<const float4 *>(r) + lane);
-        float4 o;
-        if (MODEL == BLP_MODEL_TRANSE) {
-            o.x = fabsf(fsub(fadd(hv.x, rv.x), tv.x)); o.y = fabsf(fsub(fadd(hv.y, rv.y), tv.y));
-            o.z = fabsf(fsub(fadd(hv.z, rv.z), tv.z)); o.w = fabsf(fsub(fadd(hv.w, rv.w), tv.w));
-        } else {
-            o.x = fmul(fmul(hv.x, rv.x), tv.x); o.y = fmul(fmul(hv.y, rv.y), tv.y);
-            o.z = fmul(fmul(hv.z, rv.z), tv.z); o.w = fmul(fmul(hv.w, rv.w), tv.w);
-        }
-        reinterpret_cast<float4 *>(tm)[lane] = o;
-    } else {
-        // halves: lane owns positions 2 * lane, 2 * lane + 1 of [0, 64)
-        const float2 h0 = __ldg(reinterpret_cast<const float2 *>(h) + lane), h1 = __ldg(reinterpret_cast<const float2 *>(h + L) + lane);
-        const float2 t0 = __ldg(reinterpret_cast<const float2 *>(t) + lane), t1 = __ldg(reinterpret_cast<const float2 *>(t + L) + lane);
-        const float2 r0 = __ldg(reinterpret_cast<const float2 *>(r) + lane), r1 = __ldg(reinterpret_cast<const float2 *>(r + L) + lane);
-        const float hx[2] = {h0.x, h0.y}, hy[2] = {h1.x, h1.y}, tx[2] = {t0.x, t0.y}, ty[2] = {t1.x, t1.y};
-        const float rx[2] = {r0.x, r0.y}, ry[2] = {r1.x, r1.y};
-        float o[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (MODEL == BLP_MODEL_COMPLEX) {        // models.py:230-239, left to right
-                float p = fadd(fmul(fmul(rx[u], hx[u]), tx[u]), fmul(fmul(rx[u], hy[u]), ty[u]));
-                p = fadd(p, fmul(fmul(ry[u], hx[u]), ty[u]));
-                o[u] = fsub(p, fmul(fmul(ry[u], hy[u]), tx[u]));
-            } else {                                  // models.py:242-248
-                o[u] = fadd(fmul(fmul(hx[u], rx[u]), ty[u]), fmul(fmul(tx[u], ry[u]), hy[u]));
-            }
-        }
-        reinterpret_cast<float2 *>(tm)[lane] = make_float2(o[0], o[1]);
-    }
-    __syncwarp();
-    float s = 0.0f;
-    if (MODEL == BLP_MODEL_TRANSE) {
-        if (lane == 0) {
-#pragma unroll 8
-            for (int j = 0; j < kD; j += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(tm + j);
-                s = fadd(fadd(fadd(fadd(s, v.x), v.y), v.z), v.w);
-            }
-            s = -s;
-        }
-    } else {
-        // element j -> lane j % 8, accumulator (j / 8) % 4, in increasing j (L / 32 steps per accumulator)
-        float c = 0.0f;
-        if (lane < 8) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < L / 32; ++k)
-#pragma unroll
-                for (int a = 0; a < 4; ++a) acc[a] = fadd(acc[a], tm[32 * k + 8 * a + lane]);
-            c = fadd(fadd(fadd(acc[0], acc[1]), acc[2]), acc[3]);
-        }
-#pragma unroll
-        for (int l = 0; l < 8; ++l) s = fadd(s, __shfl_sync(0xffffffffu, c, l));
-        if (MODEL == BLP_MODEL_SIMPLE) s = fmul(s, 0.5f);
-    }
+    float s = true_score_warp128<MODEL>(hr.row(i, kD), tr.row(i, kD), rr.row(i, kD), terms[warp], lane);
     if (lane == 0) {
         if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
         true_score[i] = s;
@@ -309,7 +249,11 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
                      cudaStream_t st, const long long *triples = nullptr, const void *fast_table_ws = nullptr,
                      void *fast_query_ws = nullptr, float *fast_scores = nullptr, long long fast_ld = 0) {
     const bool rows_aligned = aligned16(h.base) && aligned16(t.base) && aligned16(r.base);
-    if (d == kD && rows_aligned) {
+    // tensor-core mode folds the true-score computation into its query-folding kernel (one launch less)
+    const bool fused_true = fast_table_ws && n_local > 0 && d == kD && rows_aligned;
+    if (fused_true) {
+        // nothing to launch here
+    } else if (d == kD && rows_aligned) {
         const unsigned blocks = (unsigned)((b + kTrue128Warps - 1) / kTrue128Warps);
         switch (model) {
         case BLP_MODEL_TRANSE: true_score128_kernel<BLP_MODEL_TRANSE><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
@@ -317,19 +261,20 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
         case BLP_MODEL_COMPLEX: true_score128_kernel<BLP_MODEL_COMPLEX><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
         default: true_score128_kernel<BLP_MODEL_SIMPLE><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
         }
+        count_launch();
     } else {
         const size_t ts_smem = (size_t)kTrueWarps * 3 * d * sizeof(float);
         const int staged = ts_smem <= 48 * 1024;
         true_score_kernel<<<(unsigned)((b + kTrueWarps - 1) / kTrueWarps), kTrueWarps * 32, staged ? ts_smem : 0, st>>>(
             model, h, t, r, b, tail_off, d, staged, true_score, gt, ge);
+        count_launch();
     }
-    count_launch();
     BLP_CUDA(cudaGetLastError());
 
     if (n_local > 0 && fast_table_ws) {
-        // tensor-core mode: scores as a 3xTF32 contraction on tcgen05, same counters (blp_fast.cu)
+        // tensor-core mode: scores as a split-FP16 contraction on tcgen05, same counters (blp_fast.cu)
         const int rc = launch_fast_sweep(model, n_local, ent_offset, h, t, r, triples, b, tail_off, true_score, gt, ge,
-                                         fast_table_ws, fast_query_ws, fast_scores, fast_ld, st);
+                                         fast_table_ws, fast_query_ws, fast_scores, fast_ld, fused_true, st);
         if (rc) return rc;
     } else if (n_local > 0) {
         if (d == kD && aligned16(ent)) {

@@ -222,13 +222,18 @@ __device__ __forceinline__ float fold_coeff(bool head_pred, const float *__restr
 }
 
 // One CTA of 128 threads per query row: rows [0, b) predict heads, [b, 2b) predict tails, the rest is padding.
+// With `true_score` given, the block of head query i also produces the exact true-triple score of triple i (warp 0,
+// true_score_warp128) and resets the counters of both of its queries, which saves the separate true-score launch.
 template <int MODEL>
 __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const RowRef tr, const RowRef rr,
                                                           const long long *__restrict__ triples, long long b,
                                                           long long q_pad, __half *__restrict__ qsplit,
                                                           long long *__restrict__ self_id, float *__restrict__ qscale,
-                                                          const FastTableHeader *__restrict__ table_hdr) {
+                                                          const FastTableHeader *__restrict__ table_hdr,
+                                                          long long tail_off, float *__restrict__ true_score,
+                                                          int *__restrict__ gt, int *__restrict__ ge) {
     __shared__ float s_max[kD / 32];
+    __shared__ __align__(16) float s_terms[kD];
     const long long q = blockIdx.x;
     const int j = threadIdx.x;
     float c = 0.0f;
@@ -236,8 +241,19 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
     if (q < 2 * b) {
         const bool head_pred = q < b;
         const long long i = head_pred ? q : q - b;
-        c = fold_coeff<MODEL>(head_pred, hr.row(i, kD), tr.row(i, kD), rr.row(i, kD), j);
+        const float *h = hr.row(i, kD), *t = tr.row(i, kD), *r = rr.row(i, kD);
+        c = fold_coeff<MODEL>(head_pred, h, t, r, j);
         self = triples[i * 3 + (head_pred ? 0 : 1)];
+        if (true_score && head_pred && j < 32) {
+            float s = true_score_warp128<MODEL>(h, t, r, s_terms, j);
+            if (j == 0) {
+                if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
+                true_score[i] = s;
+                true_score[tail_off + i] = s;
+                gt[i] = 0; gt[tail_off + i] = 0;
+                ge[i] = 0; ge[tail_off + i] = 0;
+            }
+        }
     }
     // per-row power-of-two scale from the row's max |c|
     float m = fabsf(c);
@@ -541,11 +557,13 @@ static int num_sms_fast() {
     return n > 0 ? n : 148;
 }
 
-// Folds the queries, then counts gt / ge over this shard with the tcgen05 kernel.  gt / ge / true_score must
-// already hold zeros / the exact true scores (true_score_kernel has run on the same stream).
+// Folds the queries, then counts gt / ge over this shard with the tcgen05 kernel.  With compute_true the fold kernel
+// also writes the exact true scores and zeroes the counters; otherwise gt / ge / true_score must already hold zeros /
+// the exact true scores (a true-score kernel has run on the same stream).
 int launch_fast_sweep(int model, long long n_local, long long ent_offset, const RowRef &h, const RowRef &t, const RowRef &r,
-                      const long long *triples, long long b, long long tail_off, const float *true_score, int *gt, int *ge,
-                      const void *table_ws, void *query_ws, float *scores_out, long long ld_scores, cudaStream_t st) {
+                      const long long *triples, long long b, long long tail_off, float *true_score, int *gt, int *ge,
+                      const void *table_ws, void *query_ws, float *scores_out, long long ld_scores, bool compute_true,
+                      cudaStream_t st) {
     if (model != BLP_MODEL_DISTMULT && model != BLP_MODEL_COMPLEX && model != BLP_MODEL_SIMPLE) {
         set_error("fast (tensor-core) mode covers distmult / complex / simple; transe is an L1 distance, not a contraction");
         return BLP_EINVAL;
@@ -566,10 +584,11 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
         a.debug = e ? atoi(e) : 0;
     }
 
+    float *ts_out = compute_true ? true_score : nullptr;
     switch (model) {
-    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
-    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
-    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr); break;
+    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
+    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
+    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
     }
     count_launch();
     BLP_CUDA(cudaGetLastError());

@@ -28,6 +28,9 @@ SYMBOLS = {
     "blp_eval_rank": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "blp_rank_sweep": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_true_scores": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "blp_rank_sweep_counts": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
+                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "blp_fast_table_bytes": (_i64, [_i64]),
     "blp_fast_query_bytes": (_i64, [_i64]),
     "blp_fast_prepare_table": (_i32, [_vp, _i64, _i32, _vp, _vp]),

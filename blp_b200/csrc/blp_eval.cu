@@ -247,11 +247,12 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
                      const RowRef &t, const RowRef &r, int64_t b, int64_t tail_off, const int64_t *filt_indptr,
                      const int64_t *filt_idx, int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
                      cudaStream_t st, const long long *triples = nullptr, const void *fast_table_ws = nullptr,
-                     void *fast_query_ws = nullptr, float *fast_scores = nullptr, long long fast_ld = 0) {
+                     void *fast_query_ws = nullptr, float *fast_scores = nullptr, long long fast_ld = 0,
+                     int phases = 3 /* bit 0: true scores + counter reset, bit 1: sweep (+ filter correction) */) {
     const bool rows_aligned = aligned16(h.base) && aligned16(t.base) && aligned16(r.base);
     // tensor-core mode folds the true-score computation into its query-folding kernel (one launch less)
-    const bool fused_true = fast_table_ws && n_local > 0 && d == kD && rows_aligned;
-    if (fused_true) {
+    const bool fused_true = (phases & 1) && (phases & 2) && fast_table_ws && n_local > 0 && d == kD && rows_aligned;
+    if (fused_true || !(phases & 1)) {
         // nothing to launch here
     } else if (d == kD && rows_aligned) {
         const unsigned blocks = (unsigned)((b + kTrue128Warps - 1) / kTrue128Warps);
@@ -270,6 +271,7 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
         count_launch();
     }
     BLP_CUDA(cudaGetLastError());
+    if (!(phases & 2)) return BLP_OK;
 
     if (n_local > 0 && fast_table_ws) {
         // tensor-core mode: scores as a split-FP16 contraction on tcgen05, same counters (blp_fast.cu)
@@ -353,6 +355,50 @@ extern "C" int blp_rank_sweep(int model, const float *ent, int64_t n_local, int6
     if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
     return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
                      true_score, (cudaStream_t)stream);
+}
+
+// Chunked sweeps (the reference's eval batches): the true scores and the counter reset of ALL t triples in one
+// launch, then one sweep launch per chunk (blp_rank_sweep_counts) -- per chunk this halves the launches, which is
+// what bounds the entity-sharded Wikidata5M-scale sweep at eval batch 2 (49 us of HBM time per batch on 8 GPUs).
+extern "C" int blp_true_scores(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                               const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                               const float *h_rows, const float *t_rows, int64_t tail_off, int32_t *gt, int32_t *ge,
+                               float *true_score, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, t, n_local, ent, nullptr, nullptr, gt, ge, nullptr, nullptr, true_score);
+    if (rc) return rc;
+    if (t == 0) return BLP_OK;
+    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
+    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
+    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
+    const long long *tr = (const long long *)triples;
+    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
+    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
+    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
+    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, nullptr, nullptr, gt, ge, nullptr, nullptr,
+                     true_score, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 1);
+}
+
+extern "C" int blp_rank_sweep_counts(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                     const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                                     const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                                     const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                                     int32_t *ge_f, const float *true_score, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
+    if (rc) return rc;
+    if (t == 0) return BLP_OK;
+    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
+    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
+    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
+    const long long *tr = (const long long *)triples;
+    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
+    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
+    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
+    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
+                     const_cast<float *>(true_score), (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 2);
 }
 
 extern "C" int64_t blp_fast_table_bytes(int64_t n_local) { return fast_table_ws_bytes(n_local); }

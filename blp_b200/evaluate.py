@@ -146,13 +146,18 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
         outs = {name: counters[i] for i, name in enumerate(names)}
         outs["true_score"] = true_score
+        # a sweep cut into several chunks (the reference's eval batches): all true scores in one launch up front,
+        # then one sweep launch per chunk
+        split = mode == "exact" and T > chunk
+        if split:
+            launches += ops.true_scores(rel_model, ent_emb, rel_weight.detach(), triples, outs, h_rows, t_rows, ent_offset)
         for lo in range(0, T, chunk):
             hi = min(T, lo + chunk)
             indptr, idx = chunk_csr(lo, hi)
             launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
                                              None if h_rows is None else h_rows[lo:hi],
                                              None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
-                                             fast_table_ws=fast_table if mode == "fast" else None)
+                                             fast_table_ws=fast_table if mode == "fast" else None, counts_only=split)
             if dev_index is not None:
                 # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
                 launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,

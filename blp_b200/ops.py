@@ -240,8 +240,26 @@ def fast_table(ent):
     return ws
 
 
+def true_scores(model, ent, rel_weight, triples, out, h_rows=None, t_rows=None, ent_offset=0):
+    """blp_true_scores: true-triple scores + counter reset for ALL triples of a chunked sweep, one launch."""
+    mid = model_id(model)
+    dev = _require_cuda(ent, rel_weight, triples, h_rows, t_rows)
+    rel_weight = _f32c(rel_weight)
+    n, d = ent.shape
+    T = triples.shape[0]
+    if h_rows is not None:
+        h_rows, t_rows = _f32c(h_rows), _f32c(t_rows)
+    with _guard(dev):
+        _, stream = _enter(dev)
+        if T > 0:
+            check(lib().blp_true_scores(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
+                                        _ptr(triples), T, _ptr(h_rows), _ptr(t_rows), T, _ptr(out["gt"]), _ptr(out["ge"]),
+                                        _ptr(out["true_score"]), stream), "blp_true_scores")
+    return _lib.last_launch_count() if T > 0 else 0
+
+
 def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, t_rows=None, filt_indptr=None,
-                     filt_idx=None, ent_offset=0, fast_table_ws=None, scores_out=None):
+                     filt_idx=None, ent_offset=0, fast_table_ws=None, scores_out=None, counts_only=False):
     """blp_rank_sweep on triples[lo:hi], written straight into the (2, T) arrays of `out`.
 
     triples (T, 3) int64 contiguous on the device: (head row, tail row, relation id); `out` holds
@@ -285,7 +303,9 @@ def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, 
                       _ptr(filt_indptr), _ptr(filt_idx), T, at("gt"), at("ge"),
                       at("gt_f") if filt_indptr is not None else None,
                       at("ge_f") if filt_indptr is not None else None, at("true_score"))
-            if fast_table_ws is None:
+            if fast_table_ws is None and counts_only:
+                check(lib().blp_rank_sweep_counts(*common, stream), "blp_rank_sweep_counts")
+            elif fast_table_ws is None:
                 check(lib().blp_rank_sweep(*common, stream), "blp_rank_sweep")
             else:
                 # tensor-core mode (distmult / complex / simple, d = 128): tolerance-classified parity

@@ -122,6 +122,20 @@ int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_off
                    const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
                    int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score, void *stream);
 
+/* The two phases of blp_rank_sweep as separate calls, for sweeps processed in chunks (the reference's eval
+ * batches, train.py:128): blp_true_scores writes true_score and zeroes gt / ge for ALL t triples of the sweep in
+ * one launch; blp_rank_sweep_counts then counts one chunk per call (it expects true_score / zeroed counters in
+ * place and launches only the sweep, plus the CSR filter correction when filters are given). */
+int blp_true_scores(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                    const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                    const float *h_rows, const float *t_rows, int64_t tail_off, int32_t *gt, int32_t *ge,
+                    float *true_score, void *stream);
+int blp_rank_sweep_counts(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                          const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                          const float *h_rows, const float *t_rows,
+                          const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
+                          int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, const float *true_score, void *stream);
+
 /* ---- tensor-core ("fast") mode of the sweep: distmult / complex / simple, d = 128 ----
  * The bilinear scores are linear in the candidate row once the query side is folded
  * (models.py:226-248 with the candidate factored out), so the sweep is a (2t x 128) x (128 x n)

@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
         // TransE, mixed role: do this slot's head-prediction triples share one relation row?  (warp-uniform)
         bool shared_r = false;
-        if (MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2) {
+        if (MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
             const long long tr0 = t0 + QM::triple(slot, 0);
             shared_r = tr0 + C::TQP <= args.b;
             if (shared_r) {
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
                 const TileView<MODEL> tv(&sm.ctile[buf][0], row_off);
-                if (QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && shared_r)
+                if (QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4 && shared_r)
                     score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
                 else if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
@@ -661,7 +661,10 @@ template <int MODEL>
 static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
     if (a.roles == 1) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 1>(a, st);   // score_fn fast path: full tiles only
     if (a.roles == 2) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 2>(a, st);
-    int cfg = a.b <= 2 ? 0 : a.b <= 4 ? 1 : a.b <= 8 ? 2 : a.b <= 16 ? 3 : 4;
+    // up to 256 triples the 16-triple groups of Cfg<4,2> give twice as many (group, tile) work items, which evens out
+    // the per-CTA shares (E = 64: 44 vs 50 us, E = 256: 110 vs 124 us); beyond that the larger register tile of
+    // Cfg<4,4> and its shared-relation path win (E = 1024 in relation order: 0.321 vs 0.390 ms)
+    int cfg = a.b <= 2 ? 0 : a.b <= 4 ? 1 : a.b <= 8 ? 2 : a.b <= 256 ? 3 : 4;
     const char *e = getenv("BLP_SWEEP_CFG");
     if (e && e[0] >= '0' && e[0] <= '4') cfg = e[0] - '0';
     switch (cfg) {

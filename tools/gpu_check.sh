@@ -12,8 +12,8 @@ echo "== bench fast distmult"; timeout 600 python bench.py --steps 50 --warmup 5
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_reference.json | cut -c1-300
 echo "== sweeps"
 rm -f gpurun_out/sweeps.txt
-for spec in "transe 1024 14541 20" "distmult 1024 14541 10" "complex 1024 40943 5" "simple 1024 14541 10" "transe 2 4800000 10" "transe 64 4800000 3" \
-            "distmult 1024 14541 20 fast" "complex 1024 40943 10 fast" "simple 1024 14541 20 fast" "distmult 8192 14541 10 fast" "distmult 64 4800000 3 fast"; do
+for spec in "transe 64 14541 30" "distmult 64 14541 30" "transe 1024 14541 20" "distmult 1024 14541 10" "complex 1024 40943 5" "simple 1024 14541 10" "transe 2 4800000 10" "transe 64 4800000 3" \
+            "distmult 64 14541 30 fast" "distmult 1024 14541 20 fast" "complex 1024 40943 10 fast" "simple 1024 14541 20 fast" "distmult 8192 14541 10 fast" "distmult 64 4800000 3 fast"; do
   timeout 300 python tools/run_sweep.py $spec 2>&1 | tail -1 | tee -a gpurun_out/sweeps.txt
 done
 echo "== train kernel"; timeout 300 python tools/run_train.py transe margin 2>&1 | tee gpurun_out/train_kernel.txt

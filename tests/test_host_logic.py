@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import golden
-from oracle import c_oracle
+from oracle import c_oracle, np_oracle
 
 import blp_b200
 from blp_b200.evaluate import _slice_csr, rank_sweep, shard_bounds
@@ -181,3 +181,32 @@ def test_gather_rows_single_process_matches_index():
     table = torch.randn(50, 8)
     idx = torch.tensor([3, 49, 0, 3])
     assert torch.equal(blp_b200.gather_rows(table, 0, idx), table[idx])
+
+
+def test_torch_port_row_restatements_are_consistent():
+    """The CPU timing baselines of the rows either side of the path (oracle/torch_port.py) agree with the host-side
+    index logic they are timed against: filter masks == TripleFilterIndex.dense_masks; sampler structure (data.py:35-81)."""
+    from oracle import torch_port
+    rng = np.random.default_rng(3)
+    n_ids, n_rel = 60, 4
+    edges = np.stack([rng.integers(0, n_ids, 500), rng.integers(0, n_ids, 500), rng.integers(0, n_rel, 500)], 1)
+    entities = torch.from_numpy(rng.permutation(n_ids)[:45].astype(np.int64))
+    ent2idx = blp_b200.make_ent2idx(entities, n_ids - 1)
+    triples = torch.from_numpy(np.stack([entities.numpy()[rng.integers(0, 45, 20)], entities.numpy()[rng.integers(0, 45, 20)],
+                                         rng.integers(0, n_rel, 20)], 1))
+    out_edges, in_edges = {}, {}
+    for h, t, r in edges.tolist():
+        out_edges.setdefault(h, []).append((h, t, r))
+        in_edges.setdefault(t, []).append((h, t, r))
+    hm, tm = torch_port.triple_filter_masks(triples, out_edges, in_edges, 45, ent2idx.tolist())
+    want_h, want_t = blp_b200.TripleFilterIndex(edges, ent2idx).dense_masks(triples, 45)
+    assert np.array_equal(hm.numpy(), want_h) and np.array_equal(tm.numpy(), want_t)
+    neg = torch_port.sample_negative_indices(8, 50)
+    assert tuple(neg.shape) == (8, 50, 2) and tuple(neg.stride()) == (2, 16, 1)
+    own = torch.arange(16).view(8, 1, 2)
+    keep = neg == own
+    assert bool((keep.sum(-1) == 1).all())                                  # exactly one side keeps the own entity
+    repl = torch.where(keep[..., 0], neg[..., 1], neg[..., 0])
+    assert bool(((repl // 2) != torch.arange(8).view(8, 1)).all())          # the other comes from another row
+    x = torch.randn(5, 128)
+    assert np.array_equal(torch_port.normalize_rows(x).numpy(), np_oracle.l2_normalize_rows(x.numpy()))

@@ -141,3 +141,37 @@ def test_relation_sorted_sweep_is_bit_identical(cuda_device):
                             heads[sel].numpy(), tails[sel].numpy())
     assert np.array_equal(c["gt"].cpu()[:, :4].reshape(-1).numpy(), co["gt"])
     assert np.array_equal(c["ge"].cpu()[:, :4].reshape(-1).numpy(), co["ge"])
+
+
+@pytest.mark.parametrize("d", (128, 768))
+def test_umls_plumbing_config(d, cuda_device):
+    """BASELINE configs[0]: UMLS-sized (135 entities, 46 relations) TransE, margin loss, regularizer 1e-2, B = 64,
+    K = 64 -- at dim 128 (BASELINE.json) and at the 768 of the bert-bow model scripts/test-umls.sh actually runs.
+    Everything is small enough for the oracle to check every number."""
+    model, n, n_rel, b, k = "transe", 135, 46, 64, 64
+    ent, rel, heads, tails, rels = make_inputs(model, n, d, b, seed=d, n_rel=n_rel)
+    dev = cuda_device
+    # eval: one batch of 64 test triples against all 135 entities
+    out = blp_b200.rank_sweep(model, ent.to(dev), rel.to(dev), torch.stack([heads, tails, rels], dim=1).to(dev))
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy())
+    for key in ("gt", "ge", "true_score"):
+        assert np.array_equal(out[key].reshape(-1).cpu().numpy(), co[key]), key
+    recip, hits = c_oracle.metrics_from_counts(co["gt"], co["ge"], [1, 3, 10])
+    assert np.array_equal(out["recip"].reshape(-1).cpu().numpy(), recip.reshape(-1))
+    assert np.array_equal(out["hits"].cpu().numpy(), hits)
+    # train: compute_loss forward + backward with the device sampler's indices
+    g = torch.Generator().manual_seed(3)
+    pairs = torch.randint(0, n, (b, 2), generator=g)
+    brels = torch.randint(0, n_rel, (b, 1), generator=g)
+    neg = blp_b200.get_negative_sampling_indices(b, k, device=dev, seed=11)
+    m = blp_b200.TransductiveLinkPrediction(d, model, "margin", n, n_rel, 1e-2).to(dev)
+    with torch.no_grad():
+        m.ent_emb.weight.copy_(ent)
+        m.rel_emb.weight.copy_(rel)
+    ent_embs = m.encode(pairs.to(dev)).detach().requires_grad_(True)
+    loss = m.compute_loss(ent_embs, brels.to(dev), neg)
+    loss.backward()
+    co = c_oracle.train_loss(model, "margin", ent_embs.detach().cpu().numpy(), rel[brels[:, 0]].numpy(), neg.cpu().numpy(), 1e-2)
+    assert abs(loss.item() - float(co["loss"])) <= 1e-5 * abs(float(co["loss"]))
+    assert np.abs(ent_embs.grad.cpu().numpy() - co["grad_ent"]).max() <= 2e-5 * np.abs(co["grad_ent"]).max()

@@ -13,6 +13,8 @@ merges them.  Integer sums are exact, so the result is identical for any world
 size.  The query rows (true head / tail rows) are exchanged once per sweep with
 a bit-preserving all-reduce (every row is owned by exactly one rank).
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -43,6 +45,17 @@ def _world(group):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev):
+    """Two side streams per device for chunk overlap (created once)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=key), torch.cuda.Stream(device=key))
+    return _SIDE_STREAMS[key]
+
+
 def gather_rows(ent_shard, ent_offset, idx, group=None):
     """Rows `idx` (global ids) of a row-sharded table, replicated on every rank (train.py:141-142).
 
@@ -64,7 +77,8 @@ def gather_rows(ent_shard, ent_offset, idx, group=None):
 
 def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, filter_triples=None,
                filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384,
-               h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None, sort_by_relation=True):
+               h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None, sort_by_relation=True,
+               overlap_chunks=True):
     """Rank every test triple against all candidate entities (train.py:128-171 for the whole sweep).
 
     rel_model   'transe' | 'distmult' | 'complex' | 'simple'
@@ -88,6 +102,9 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 (one stable argsort per sweep; the outputs come back in the caller's order).  Triples that share a relation let the kernel compute
                 fl(candidate + r) once for several head-prediction queries (~13 % fewer FP32 lane-ops); results are
                 bit-identical either way
+    overlap_chunks   exact sweeps cut into >= 4 chunks launch consecutive chunks on two alternating side streams
+                (forked from / joined to the current stream), so one chunk's kernel start-up overlaps the previous
+                chunk's tail; results are identical
     count_fn    test seam: replaces ops.eval_rank (same signature) so the sharding / collective logic can
                 be exercised without a GPU
 
@@ -151,19 +168,38 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         split = mode == "exact" and T > chunk
         if split:
             launches += ops.true_scores(rel_model, ent_emb, rel_weight.detach(), triples, outs, h_rows, t_rows, ent_offset)
-        for lo in range(0, T, chunk):
+        # consecutive chunks are independent (disjoint output slots, read-only table), so they alternate between two
+        # side streams: the launch / fold / pipeline-fill head of one chunk's kernel overlaps the tail of the previous
+        # one (8 of 55 us per batch on a 600,000-row shard at eval batch 2).  Fork / join with events, capture-safe.
+        n_chunks = (T + chunk - 1) // chunk if T else 0
+        lanes = None
+        if overlap_chunks and split and n_chunks >= 4:
+            main = torch.cuda.current_stream(dev)
+            lanes = _side_streams(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for s_ in lanes:
+                s_.wait_event(fork)
+        for ci, lo in enumerate(range(0, T, chunk)):
             hi = min(T, lo + chunk)
-            indptr, idx = chunk_csr(lo, hi)
-            launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
-                                             None if h_rows is None else h_rows[lo:hi],
-                                             None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
-                                             fast_table_ws=fast_table if mode == "fast" else None, counts_only=split)
-            if dev_index is not None:
-                # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
-                launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
-                                               dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
-                                               None if h_rows is None else h_rows[lo:hi],
-                                               None if t_rows is None else t_rows[lo:hi], ent_offset)
+            ctx = torch.cuda.stream(lanes[ci & 1]) if lanes is not None else contextlib.nullcontext()
+            with ctx:
+                indptr, idx = chunk_csr(lo, hi)         # host CSR path: its H2D copies ride the chunk's stream
+                launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
+                                                 None if h_rows is None else h_rows[lo:hi],
+                                                 None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
+                                                 fast_table_ws=fast_table if mode == "fast" else None, counts_only=split)
+                if dev_index is not None:
+                    # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
+                    launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
+                                                   dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
+                                                   None if h_rows is None else h_rows[lo:hi],
+                                                   None if t_rows is None else t_rows[lo:hi], ent_offset)
+        if lanes is not None:
+            for s_ in lanes:
+                join = torch.cuda.Event()
+                join.record(s_)
+                main.wait_event(join)
         if perm is not None:
             # back to the caller's order: slot perm[j] receives what was computed for sorted position j
             buf = torch.empty_like(buf).index_copy_(2, perm, buf)

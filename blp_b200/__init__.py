@@ -21,7 +21,7 @@ from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPr
                      complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,
                      margin_loss, nll_loss, simple_score, transe_score)
 from .utils import (DeviceFilterIndex, TripleFilterIndex, get_metrics, get_negative_sampling_indices,  # noqa: F401
-                    make_ent2idx)  # noqa: F401
+                    graph_edges, make_ent2idx)  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -31,6 +31,15 @@ SYMBOLS = {
     "blp_true_scores": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "blp_rank_sweep_counts": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_rank_step_workspace_bytes": (_i64, [_i64]),
+    "blp_rank_step": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp,
+                             ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp, _vp]),
+    "blp_plan_create": (_i32, [ctypes.POINTER(_vp), _i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,
+                               ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp]),
+    "blp_plan_run": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "blp_plan_destroy": (None, [_vp]),
+    "blp_rank_queries": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
+                                ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp, _vp]),
     "blp_fast_table_bytes": (_i64, [_i64]),
     "blp_fast_query_bytes": (_i64, [_i64]),
     "blp_fast_prepare_table": (_i32, [_vp, _i64, _i32, _vp, _vp]),
@@ -51,6 +60,7 @@ SYMBOLS = {
     "blp_negative_sample": (_i32, [_i64, _i64, _i64, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "blp_store_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i64, _vp]),
     "blp_profile_events": (_i32, [_i32, _vp, _vp]),
+    "blp_debug_timestamps": (_i32, [_vp]),
     "blp_pipe_probe": (_i32, [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

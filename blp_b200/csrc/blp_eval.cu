@@ -19,21 +19,28 @@ namespace blp {
 // replays the reference's sequential / ATen-order reduction from there (the same
 // score_exact code every other exact path uses, so all of them agree bit for bit).
 constexpr int kTrueWarps = 4;
+// `split`: head query i and tail query i are unrelated queries with their own operand rows (hr2, tr2, rr2 for the
+// tail queries); otherwise both queries of triple i share one true score.
 __global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, const RowRef hr, const RowRef tr,
-                                                                    const RowRef rr, long long b, long long tail_off,
-                                                                    int d, int staged, float *__restrict__ true_score,
+                                                                    const RowRef rr, const RowRef hr2, const RowRef tr2,
+                                                                    const RowRef rr2, int split, long long b,
+                                                                    long long tail_off, int d, int staged,
+                                                                    float *__restrict__ true_score,
                                                                     int *__restrict__ gt, int *__restrict__ ge) {
     extern __shared__ float ts_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long i = (long long)blockIdx.x * kTrueWarps + warp;
-    if (i >= b) return;
-    const float *h = hr.row(i, d), *t = tr.row(i, d), *r = rr.row(i, d);
+    const long long j = (long long)blockIdx.x * kTrueWarps + warp;
+    if (j >= (split ? 2 * b : b)) return;
+    const bool second = j >= b;
+    const long long i = second ? j - b : j;
+    const RowRef &H = second ? hr2 : hr, &T = second ? tr2 : tr, &R = second ? rr2 : rr;
+    const float *h = H.row(i, d), *t = T.row(i, d), *r = R.row(i, d);
     if (staged) {
         float *sh = ts_smem + (size_t)warp * 3 * d, *stt = sh + d, *sr = stt + d;
-        for (int j = lane; j < d; j += 32) {
-            sh[j] = h[j];
-            stt[j] = t[j];
-            sr[j] = r[j];
+        for (int jj = lane; jj < d; jj += 32) {
+            sh[jj] = h[jj];
+            stt[jj] = t[jj];
+            sr[jj] = r[jj];
         }
         __syncwarp();
         h = sh; t = stt; r = sr;
@@ -42,11 +49,9 @@ __global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, 
         float s = score_exact_dyn(model, h, t, r, d);
         // an index outside the table (train.py:137-138 asserts this never happens): NaN compares false
         // against every candidate, so the query reports gt = ge = 0 and is detectable
-        if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
-        true_score[i] = s;
-        true_score[tail_off + i] = s;
-        gt[i] = 0; gt[tail_off + i] = 0;
-        ge[i] = 0; ge[tail_off + i] = 0;
+        if (!(H.in_range(i) && T.in_range(i) && R.in_range(i))) s = __int_as_float(0x7fc00000);
+        if (!split || !second) { true_score[i] = s; gt[i] = 0; ge[i] = 0; }
+        if (!split || second) { true_score[tail_off + i] = s; gt[tail_off + i] = 0; ge[tail_off + i] = 0; }
     }
 }
 
@@ -58,20 +63,22 @@ __global__ void __launch_bounds__(kTrueWarps * 32) true_score_kernel(int model, 
 constexpr int kTrue128Warps = 8;
 template <int MODEL>
 __global__ void __launch_bounds__(kTrue128Warps * 32) true_score128_kernel(const RowRef hr, const RowRef tr, const RowRef rr,
-                                                                           long long b, long long tail_off,
+                                                                           const RowRef hr2, const RowRef tr2, const RowRef rr2,
+                                                                           int split, long long b, long long tail_off,
                                                                            float *__restrict__ true_score,
                                                                            int *__restrict__ gt, int *__restrict__ ge) {
     __shared__ __align__(16) float terms[kTrue128Warps][kD];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long i = (long long)blockIdx.x * kTrue128Warps + warp;
-    if (i >= b) return;
-    float s = true_score_warp128<MODEL>(hr.row(i, kD), tr.row(i, kD), rr.row(i, kD), terms[warp], lane);
+    const long long j = (long long)blockIdx.x * kTrue128Warps + warp;
+    if (j >= (split ? 2 * b : b)) return;
+    const bool second = j >= b;
+    const long long i = second ? j - b : j;
+    const RowRef &H = second ? hr2 : hr, &T = second ? tr2 : tr, &R = second ? rr2 : rr;
+    float s = true_score_warp128<MODEL>(H.row(i, kD), T.row(i, kD), R.row(i, kD), terms[warp], lane);
     if (lane == 0) {
-        if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
-        true_score[i] = s;
-        true_score[tail_off + i] = s;
-        gt[i] = 0; gt[tail_off + i] = 0;
-        ge[i] = 0; ge[tail_off + i] = 0;
+        if (!(H.in_range(i) && T.in_range(i) && R.in_range(i))) s = __int_as_float(0x7fc00000);
+        if (!split || !second) { true_score[i] = s; gt[i] = 0; ge[i] = 0; }
+        if (!split || second) { true_score[tail_off + i] = s; gt[tail_off + i] = 0; ge[tail_off + i] = 0; }
     }
 }
 
@@ -113,14 +120,15 @@ __global__ void filter_correct_kernel(int model, const float *__restrict__ ent, 
 
 // ---- generic-width sweep (d != 128): one thread per (query, candidate) -----
 __global__ void sweep_generic_kernel(int model, const float *__restrict__ ent, long long n_local, int d, const RowRef hr,
-                                     const RowRef tr, const RowRef rr, long long b, long long tail_off,
+                                     const RowRef tr, const RowRef rr, const RowRef hr2, const RowRef tr2, const RowRef rr2,
+                                     long long b, long long tail_off,
                                      const float *__restrict__ true_score, int *__restrict__ gt, int *__restrict__ ge) {
     for (long long q = blockIdx.y; q < 2 * b; q += gridDim.y) {
         const bool head_pred = q < b;
         const long long i = head_pred ? q : q - b;
         const long long o = head_pred ? i : tail_off + i;
         const float st = true_score[o];
-        const float *h = hr.row(i, d), *t = tr.row(i, d), *r = rr.row(i, d);
+        const float *h = (head_pred ? hr : hr2).row(i, d), *t = (head_pred ? tr : tr2).row(i, d), *r = (head_pred ? rr : rr2).row(i, d);
         int cg = 0, ce = 0;
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_local; c += (long long)gridDim.x * blockDim.x) {
             const float *e = ent + c * d;
@@ -154,7 +162,10 @@ __global__ void rank_counts_kernel(const float *__restrict__ pred, long long n, 
                                    const long long *__restrict__ true_idx, int *__restrict__ gt, int *__restrict__ ge) {
     const long long q = blockIdx.x;
     const float *row = pred + q * row_stride;
-    const float st = row[true_idx[q]];
+    // torch.gather raises on an out-of-range index (utils.py:103); a device kernel cannot, so the query is flagged
+    // instead: NaN compares false against every score -> gt = ge = 0 (reciprocal rank 2.0, an impossible value)
+    const long long ti = true_idx[q];
+    const float st = (ti >= 0 && ti < n) ? row[ti] : __int_as_float(0x7fc00000);
     int cg = 0, ce = 0;
     for (long long j = threadIdx.x; j < n; j += blockDim.x) {
         const float s = row[j];
@@ -176,7 +187,6 @@ __global__ void rank_counts_kernel(const float *__restrict__ pred, long long n, 
     }
 }
 
-struct KValues { long long k[8]; int nk; };
 // utils.py:106-109: avg = float(best + worst) * 0.5; 1 / avg; avg <= k
 __global__ void metrics_kernel(const int *__restrict__ gt, const int *__restrict__ ge, long long q, KValues kv,
                                float *__restrict__ recip, unsigned char *__restrict__ hits) {
@@ -242,48 +252,86 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 using namespace blp;
 
+// One ranking problem: `b` head-prediction queries (operand rows h, t, r; the candidate plays `heads`, train.py:146)
+// and `b` tail-prediction queries (rows h2, t2, r2; train.py:147).  In the reference's eval loop both come from the
+// same b triples (split == 0: h2 == h, ...); the score-matrix path ranks unrelated queries (split == 1).
+struct RankJob {
+    int model;
+    const float *ent; long long n_local, ent_offset; int d;
+    RowRef h, t, r, h2, t2, r2; int split;
+    long long b, tail_off;
+    const long long *filt_indptr, *filt_idx;      // legacy CSR filter lists (triple mode only)
+    int *gt, *ge, *gt_f, *ge_f; float *true_score;
+    int roles;                                     // 3 both, 1 head queries only, 2 tail queries only (d == 128 only)
+    int force_cfg;                                 // -1 auto
+    // tensor-core mode
+    const long long *triples; const void *fast_table_ws; void *fast_query_ws; float *fast_scores; long long fast_ld;
+    int phases;                                    // bit 0: true scores + counter reset, bit 1: sweep (+ CSR filter correction)
+};
+
+static RankJob make_job(int model, const float *ent, long long n_local, long long ent_offset, int d, const RowRef &h,
+                        const RowRef &t, const RowRef &r, long long b, long long tail_off, int *gt, int *ge,
+                        float *true_score) {
+    RankJob j{};
+    j.model = model; j.ent = ent; j.n_local = n_local; j.ent_offset = ent_offset; j.d = d;
+    j.h = h; j.t = t; j.r = r; j.h2 = h; j.t2 = t; j.r2 = r; j.split = 0;
+    j.b = b; j.tail_off = tail_off; j.gt = gt; j.ge = ge; j.true_score = true_score;
+    j.roles = 3; j.force_cfg = -1; j.phases = 3;
+    return j;
+}
+
+static void fill_sweep_args(SweepArgs &a, const RankJob &j) {
+    a.ent = j.ent; a.n_local = j.n_local; a.h = j.h; a.t = j.t; a.r = j.r; a.h2 = j.h2; a.t2 = j.t2; a.r2 = j.r2;
+    a.split_sets = j.split; a.b = j.b; a.tail_off = j.tail_off; a.true_score = j.true_score; a.gt = j.gt; a.ge = j.ge;
+    a.scores_out = nullptr; a.ld_scores = 0; a.roles = j.roles; a.groups = 0; a.use_tma = sweep_env_use_tma();
+    a.force_cfg = j.force_cfg; a.negzero2 = kNegZero2;
+}
+
+static bool job_rows_aligned(const RankJob &j) {
+    return aligned16(j.h.base) && aligned16(j.t.base) && aligned16(j.r.base) && aligned16(j.h2.base) &&
+           aligned16(j.t2.base) && aligned16(j.r2.base);
+}
+
 // Shared body of blp_eval_rank / blp_rank_sweep: true scores (+ counter reset), the sweep, the filter correction.
-static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d, const RowRef &h,
-                     const RowRef &t, const RowRef &r, int64_t b, int64_t tail_off, const int64_t *filt_indptr,
-                     const int64_t *filt_idx, int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
-                     cudaStream_t st, const long long *triples = nullptr, const void *fast_table_ws = nullptr,
-                     void *fast_query_ws = nullptr, float *fast_scores = nullptr, long long fast_ld = 0,
-                     int phases = 3 /* bit 0: true scores + counter reset, bit 1: sweep (+ filter correction) */) {
-    const bool rows_aligned = aligned16(h.base) && aligned16(t.base) && aligned16(r.base);
+static int rank_impl(const RankJob &j, cudaStream_t st) {
+    const int model = j.model, d = j.d;
+    const long long b = j.b, tail_off = j.tail_off, n_local = j.n_local;
+    const bool rows_aligned = job_rows_aligned(j);
     // tensor-core mode folds the true-score computation into its query-folding kernel (one launch less)
-    const bool fused_true = (phases & 1) && (phases & 2) && fast_table_ws && n_local > 0 && d == kD && rows_aligned;
-    if (fused_true || !(phases & 1)) {
+    const bool fused_true = (j.phases & 1) && (j.phases & 2) && j.fast_table_ws && n_local > 0 && d == kD && rows_aligned;
+    const long long jobs = j.split ? 2 * b : b;
+    if (fused_true || !(j.phases & 1)) {
         // nothing to launch here
     } else if (d == kD && rows_aligned) {
-        const unsigned blocks = (unsigned)((b + kTrue128Warps - 1) / kTrue128Warps);
+        const unsigned blocks = (unsigned)((jobs + kTrue128Warps - 1) / kTrue128Warps);
+#define BLP_TS128(M) true_score128_kernel<M><<<blocks, kTrue128Warps * 32, 0, st>>>(j.h, j.t, j.r, j.h2, j.t2, j.r2, j.split, b, tail_off, j.true_score, j.gt, j.ge)
         switch (model) {
-        case BLP_MODEL_TRANSE: true_score128_kernel<BLP_MODEL_TRANSE><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
-        case BLP_MODEL_DISTMULT: true_score128_kernel<BLP_MODEL_DISTMULT><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
-        case BLP_MODEL_COMPLEX: true_score128_kernel<BLP_MODEL_COMPLEX><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
-        default: true_score128_kernel<BLP_MODEL_SIMPLE><<<blocks, kTrue128Warps * 32, 0, st>>>(h, t, r, b, tail_off, true_score, gt, ge); break;
+        case BLP_MODEL_TRANSE: BLP_TS128(BLP_MODEL_TRANSE); break;
+        case BLP_MODEL_DISTMULT: BLP_TS128(BLP_MODEL_DISTMULT); break;
+        case BLP_MODEL_COMPLEX: BLP_TS128(BLP_MODEL_COMPLEX); break;
+        default: BLP_TS128(BLP_MODEL_SIMPLE); break;
         }
+#undef BLP_TS128
         count_launch();
     } else {
         const size_t ts_smem = (size_t)kTrueWarps * 3 * d * sizeof(float);
         const int staged = ts_smem <= 48 * 1024;
-        true_score_kernel<<<(unsigned)((b + kTrueWarps - 1) / kTrueWarps), kTrueWarps * 32, staged ? ts_smem : 0, st>>>(
-            model, h, t, r, b, tail_off, d, staged, true_score, gt, ge);
+        true_score_kernel<<<(unsigned)((jobs + kTrueWarps - 1) / kTrueWarps), kTrueWarps * 32, staged ? ts_smem : 0, st>>>(
+            model, j.h, j.t, j.r, j.h2, j.t2, j.r2, j.split, b, tail_off, d, staged, j.true_score, j.gt, j.ge);
         count_launch();
     }
     BLP_CUDA(cudaGetLastError());
-    if (!(phases & 2)) return BLP_OK;
+    if (!(j.phases & 2)) return BLP_OK;
 
-    if (n_local > 0 && fast_table_ws) {
+    if (n_local > 0 && j.fast_table_ws) {
         // tensor-core mode: scores as a split-FP16 contraction on tcgen05, same counters (blp_fast.cu)
-        const int rc = launch_fast_sweep(model, n_local, ent_offset, h, t, r, triples, b, tail_off, true_score, gt, ge,
-                                         fast_table_ws, fast_query_ws, fast_scores, fast_ld, fused_true, st);
+        const int rc = launch_fast_sweep(model, n_local, j.ent_offset, j.h, j.t, j.r, j.triples, b, tail_off, j.true_score,
+                                         j.gt, j.ge, j.fast_table_ws, j.fast_query_ws, j.fast_scores, j.fast_ld, fused_true, st);
         if (rc) return rc;
     } else if (n_local > 0) {
-        if (d == kD && aligned16(ent)) {
+        if (d == kD && aligned16(j.ent)) {
             SweepArgs a{};
-            a.ent = ent; a.n_local = n_local; a.h = h; a.t = t; a.r = r; a.b = b; a.tail_off = tail_off;
-            a.true_score = true_score; a.gt = gt; a.ge = ge; a.scores_out = nullptr; a.ld_scores = 0;
-            a.roles = 3; a.groups = 0; a.use_tma = sweep_env_use_tma(); a.negzero2 = kNegZero2;
+            fill_sweep_args(a, j);
             const int rc = launch_sweep_dyn(model, a, st);
             if (rc) return rc;
         } else {
@@ -292,18 +340,79 @@ static int rank_impl(int model, const float *ent, int64_t n_local, int64_t ent_o
             if (bx > 1024) bx = 1024;
             const long long by = 2 * b < 65535 ? 2 * b : 65535;
             dim3 grid((unsigned)bx, (unsigned)by);
-            sweep_generic_kernel<<<grid, threads, 0, st>>>(model, ent, n_local, d, h, t, r, b, tail_off, true_score, gt, ge);
+            sweep_generic_kernel<<<grid, threads, 0, st>>>(model, j.ent, n_local, d, j.h, j.t, j.r, j.h2, j.t2, j.r2, b, tail_off,
+                                                           j.true_score, j.gt, j.ge);
             count_launch();
             BLP_CUDA(cudaGetLastError());
         }
     }
-    if (gt_f && ge_f) {
+    if (j.gt_f && j.ge_f) {
         const long long warps = 2 * b;
         const int threads = 128;
         const long long blocks = (warps * 32 + threads - 1) / threads;
-        filter_correct_kernel<<<(unsigned)blocks, threads, 0, st>>>(model, ent, n_local, ent_offset, d, h, t, r, b, tail_off,
-                                                                    (const long long *)filt_indptr,
-                                                                    (const long long *)filt_idx, true_score, gt, ge, gt_f, ge_f);
+        filter_correct_kernel<<<(unsigned)blocks, threads, 0, st>>>(model, j.ent, n_local, j.ent_offset, d, j.h, j.t, j.r, b, tail_off,
+                                                                    j.filt_indptr, j.filt_idx, j.true_score, j.gt, j.ge, j.gt_f, j.ge_f);
+        count_launch();
+        BLP_CUDA(cudaGetLastError());
+    }
+    return BLP_OK;
+}
+
+// ---- one launch per eval batch ---------------------------------------------------------------------
+// Workspace of the fused step: a CTA ticket, then two zero-invariant int32 accumulator arrays of out_len entries.
+static long long step_ws_bytes(long long out_len) { return 64 + 8 * (out_len > 0 ? out_len : 0); }
+constexpr long long kFusedEpilogueMax = 16384;    // the last CTA walks the whole output range: keep that short
+
+struct StepOut {
+    KValues kv; float *recip; unsigned char *hits; double *sums;     // optional metrics (sums == NULL: none)
+    void *workspace;
+};
+
+// True scores, sweep and (optionally) the metrics of one batch.  d == 128 on a non-empty shard with a workspace:
+// ONE launch (true scores per group inside the sweep kernel, last-CTA epilogue); otherwise the separate kernels.
+static int rank_step_impl(RankJob j, const StepOut &o, cudaStream_t st) {
+    const long long out_len = j.roles == 3 ? j.tail_off + j.b : j.b;  // single-role passes write [0, b) only
+    const bool dense_out = j.roles == 3 && j.tail_off == j.b;        // metrics kernels walk [0, 2b)
+    const bool tiled = j.d == kD && j.n_local > 0 && aligned16(j.ent) && job_rows_aligned(j) && !j.fast_table_ws;
+    if (tiled) {
+        SweepArgs a{};
+        fill_sweep_args(a, j);
+        a.true_score = nullptr;
+        a.fuse_true = 1;
+        a.true_score_out = j.true_score;
+        a.out_len = out_len;
+        const bool epi = o.workspace && out_len <= kFusedEpilogueMax && (dense_out || !o.sums);
+        if (epi) {
+            unsigned char *ws = reinterpret_cast<unsigned char *>(o.workspace);
+            a.fuse_epilogue = 1;
+            a.ticket = reinterpret_cast<unsigned int *>(ws);
+            a.gt = reinterpret_cast<int *>(ws + 64);
+            a.ge = a.gt + out_len;
+            a.gt_out = j.gt; a.ge_out = j.ge;
+            a.kv = o.kv; a.recip = o.recip; a.hits = o.hits; a.sums = o.sums;
+            return launch_sweep_dyn(j.model, a, st);
+        }
+        // long output ranges: counters zeroed by a memset, metrics by their own kernel
+        if (dense_out || j.roles != 3) {
+            BLP_CUDA(cudaMemsetAsync(j.gt, 0, sizeof(int) * out_len, st));
+            BLP_CUDA(cudaMemsetAsync(j.ge, 0, sizeof(int) * out_len, st));
+        } else {
+            BLP_CUDA(cudaMemsetAsync(j.gt, 0, sizeof(int) * j.b, st));
+            BLP_CUDA(cudaMemsetAsync(j.gt + j.tail_off, 0, sizeof(int) * j.b, st));
+            BLP_CUDA(cudaMemsetAsync(j.ge, 0, sizeof(int) * j.b, st));
+            BLP_CUDA(cudaMemsetAsync(j.ge + j.tail_off, 0, sizeof(int) * j.b, st));
+        }
+        const int rc = launch_sweep_dyn(j.model, a, st);
+        if (rc) return rc;
+    } else {
+        if (j.roles != 3) { set_error("single-role ranking needs d == 128 rows that are 16-byte aligned"); return BLP_EDIM; }
+        j.phases = 3;
+        const int rc = rank_impl(j, st);
+        if (rc) return rc;
+    }
+    if (o.sums) {
+        if (!dense_out) { set_error("metrics need contiguous outputs (tail_off == t)"); return BLP_EINVAL; }
+        metrics_reduce_kernel<<<1, 1024, 0, st>>>(j.gt, j.ge, 2 * j.b, o.kv, o.recip, o.hits, o.sums);
         count_launch();
         BLP_CUDA(cudaGetLastError());
     }
@@ -322,6 +431,27 @@ static int check_rank_args(int model, int d, int64_t b, int64_t n_local, const v
     return BLP_OK;
 }
 
+// gather views of the query rows (train.py:141-143 folded into the kernels)
+struct TripleRows { RowRef h, t, r; };
+static TripleRows triple_rows(const float *ent, int64_t n_local, int64_t ent_offset, const float *rel_weight, int64_t num_rel,
+                              const int64_t *triples, const float *h_rows, const float *t_rows) {
+    const long long *tr = (const long long *)triples;
+    TripleRows q;
+    q.h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
+    q.t = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
+    q.r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
+    return q;
+}
+
+static int check_sweep_args(const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t, const float *h_rows,
+                            const float *t_rows, int64_t tail_off, int64_t n_local) {
+    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
+    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
+    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
+    return BLP_OK;
+}
+
 extern "C" int blp_eval_rank(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
                              const float *h_rows, const float *t_rows, const float *r_rows, int64_t b,
                              const int64_t *filt_indptr, const int64_t *filt_idx, int32_t *gt, int32_t *ge,
@@ -331,8 +461,10 @@ extern "C" int blp_eval_rank(int model, const float *ent, int64_t n_local, int64
     if (rc) return rc;
     if (b == 0) return BLP_OK;
     if (!h_rows || !t_rows || !r_rows) { set_error("null pointer argument"); return BLP_EINVAL; }
-    return rank_impl(model, ent, n_local, ent_offset, d, dense_rows(h_rows), dense_rows(t_rows), dense_rows(r_rows), b, b,
-                     filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score, (cudaStream_t)stream);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, dense_rows(h_rows), dense_rows(t_rows), dense_rows(r_rows), b, b,
+                         gt, ge, true_score);
+    j.filt_indptr = (const long long *)filt_indptr; j.filt_idx = (const long long *)filt_idx; j.gt_f = gt_f; j.ge_f = ge_f;
+    return rank_impl(j, (cudaStream_t)stream);
 }
 
 extern "C" int blp_rank_sweep(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
@@ -344,22 +476,15 @@ extern "C" int blp_rank_sweep(int model, const float *ent, int64_t n_local, int6
     int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
     if (rc) return rc;
     if (t == 0) return BLP_OK;
-    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
-    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
-    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
-    const long long *tr = (const long long *)triples;
-    // train.py:141-143: head_embs = ent_emb[heads], tail_embs = ent_emb[tails], rel_embs = rel_emb(rels)
-    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
-    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
-    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
-    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
-    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
-                     true_score, (cudaStream_t)stream);
+    if ((rc = check_sweep_args(rel_weight, num_rel, triples, t, h_rows, t_rows, tail_off, n_local))) return rc;
+    const TripleRows q = triple_rows(ent, n_local, ent_offset, rel_weight, num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, q.h, q.t, q.r, t, tail_off, gt, ge, true_score);
+    j.filt_indptr = (const long long *)filt_indptr; j.filt_idx = (const long long *)filt_idx; j.gt_f = gt_f; j.ge_f = ge_f;
+    return rank_impl(j, (cudaStream_t)stream);
 }
 
 // Chunked sweeps (the reference's eval batches): the true scores and the counter reset of ALL t triples in one
-// launch, then one sweep launch per chunk (blp_rank_sweep_counts) -- per chunk this halves the launches, which is
-// what bounds the entity-sharded Wikidata5M-scale sweep at eval batch 2 (49 us of HBM time per batch on 8 GPUs).
+// launch, then one sweep launch per chunk (blp_rank_sweep_counts).
 extern "C" int blp_true_scores(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
                                const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
                                const float *h_rows, const float *t_rows, int64_t tail_off, int32_t *gt, int32_t *ge,
@@ -368,16 +493,11 @@ extern "C" int blp_true_scores(int model, const float *ent, int64_t n_local, int
     int rc = check_rank_args(model, d, t, n_local, ent, nullptr, nullptr, gt, ge, nullptr, nullptr, true_score);
     if (rc) return rc;
     if (t == 0) return BLP_OK;
-    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
-    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
-    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
-    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
-    const long long *tr = (const long long *)triples;
-    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
-    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
-    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
-    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, nullptr, nullptr, gt, ge, nullptr, nullptr,
-                     true_score, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 1);
+    if ((rc = check_sweep_args(rel_weight, num_rel, triples, t, h_rows, t_rows, tail_off, n_local))) return rc;
+    const TripleRows q = triple_rows(ent, n_local, ent_offset, rel_weight, num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, q.h, q.t, q.r, t, tail_off, gt, ge, true_score);
+    j.phases = 1;
+    return rank_impl(j, (cudaStream_t)stream);
 }
 
 extern "C" int blp_rank_sweep_counts(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
@@ -389,16 +509,137 @@ extern "C" int blp_rank_sweep_counts(int model, const float *ent, int64_t n_loca
     int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
     if (rc) return rc;
     if (t == 0) return BLP_OK;
-    if (!rel_weight || !triples || num_rel <= 0) { set_error("null pointer argument"); return BLP_EINVAL; }
-    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
-    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
-    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
-    const long long *tr = (const long long *)triples;
-    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
-    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
-    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
-    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
-                     const_cast<float *>(true_score), (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 2);
+    if ((rc = check_sweep_args(rel_weight, num_rel, triples, t, h_rows, t_rows, tail_off, n_local))) return rc;
+    const TripleRows q = triple_rows(ent, n_local, ent_offset, rel_weight, num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, q.h, q.t, q.r, t, tail_off, gt, ge, const_cast<float *>(true_score));
+    j.filt_indptr = (const long long *)filt_indptr; j.filt_idx = (const long long *)filt_idx; j.gt_f = gt_f; j.ge_f = ge_f;
+    j.phases = 2;
+    return rank_impl(j, (cudaStream_t)stream);
+}
+
+// ---- the fused step: one launch per eval batch ------------------------------------------------------
+static int fill_kvalues(KValues &kv, const int64_t *k_values_host, int nk) {
+    if (nk < 0 || nk > 8 || (nk > 0 && !k_values_host)) { set_error("bad k_values (nk <= 8)"); return BLP_EINVAL; }
+    kv.nk = nk;
+    for (int i = 0; i < nk; ++i) kv.k[i] = k_values_host[i];
+    return BLP_OK;
+}
+
+extern "C" int64_t blp_rank_step_workspace_bytes(int64_t out_len) { return step_ws_bytes(out_len); }
+
+extern "C" int blp_rank_step(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                             const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                             const float *h_rows, const float *t_rows, int64_t tail_off, int group_triples,
+                             int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                             float *recip, uint8_t *hits, double *sums, void *workspace, void *stream) {
+    reset_launch_count();
+    int rc = check_rank_args(model, d, t, n_local, ent, nullptr, nullptr, gt, ge, nullptr, nullptr, true_score);
+    if (rc) return rc;
+    if (t == 0) return BLP_OK;
+    if ((rc = check_sweep_args(rel_weight, num_rel, triples, t, h_rows, t_rows, tail_off, n_local))) return rc;
+    StepOut o{};
+    if ((rc = fill_kvalues(o.kv, k_values_host, nk))) return rc;
+    o.recip = recip; o.hits = hits; o.sums = sums; o.workspace = workspace;
+    const TripleRows q = triple_rows(ent, n_local, ent_offset, rel_weight, num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, q.h, q.t, q.r, t, tail_off, gt, ge, true_score);
+    j.force_cfg = sweep_cfg_for_group(group_triples);
+    return rank_step_impl(j, o, (cudaStream_t)stream);
+}
+
+// Everything of blp_rank_step that does not change from batch to batch, bound once (the reference's eval loop calls
+// the step every 64 triples: argument marshalling is a visible share of a 20 us step).
+struct RankPlan {
+    int model; const float *ent; int64_t n_local, ent_offset; int d; const float *rel_weight; int64_t num_rel, t, tail_off;
+    int group_triples; int32_t *gt, *ge; float *true_score; int64_t k_values[8]; int nk; float *recip; uint8_t *hits;
+    double *sums; void *workspace;
+};
+
+extern "C" int blp_plan_create(void **plan_out, int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                               const float *rel_weight, int64_t num_rel, int64_t t, int64_t tail_off, int group_triples,
+                               int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                               float *recip, uint8_t *hits, double *sums, void *workspace) {
+    if (!plan_out) { set_error("null plan_out"); return BLP_EINVAL; }
+    *plan_out = nullptr;
+    int rc = check_rank_args(model, d, t, n_local, ent, nullptr, nullptr, gt, ge, nullptr, nullptr, true_score);
+    if (rc) return rc;
+    if (nk < 0 || nk > 8 || (nk > 0 && !k_values_host)) { set_error("bad k_values (nk <= 8)"); return BLP_EINVAL; }
+    if (!rel_weight || num_rel <= 0 || tail_off < t) { set_error("bad argument"); return BLP_EINVAL; }
+    RankPlan *p = new RankPlan{model, ent, n_local, ent_offset, d, rel_weight, num_rel, t, tail_off, group_triples, gt, ge,
+                               true_score, {0}, nk, recip, hits, sums, workspace};
+    for (int i = 0; i < nk; ++i) p->k_values[i] = k_values_host[i];
+    *plan_out = p;
+    return BLP_OK;
+}
+
+extern "C" int blp_plan_run(void *plan, const int64_t *triples, const float *h_rows, const float *t_rows, void *stream) {
+    if (!plan) { set_error("null plan"); return BLP_EINVAL; }
+    const RankPlan *p = reinterpret_cast<const RankPlan *>(plan);
+    return blp_rank_step(p->model, p->ent, p->n_local, p->ent_offset, p->d, p->rel_weight, p->num_rel, triples, p->t, h_rows,
+                         t_rows, p->tail_off, p->group_triples, p->gt, p->ge, p->true_score, p->k_values, p->nk, p->recip,
+                         p->hits, p->sums, p->workspace, stream);
+}
+
+extern "C" void blp_plan_destroy(void *plan) { delete reinterpret_cast<RankPlan *>(plan); }
+
+// Ranking of unrelated queries against the table (what `get_metrics(score_fn(...), true_idx, k)` asks for when the
+// score matrix is never materialised): n_hq head-prediction queries -- candidate row e scored as
+// score_fn(e, hq_tails[i], hq_rels[i]), true candidate hq_true[i] -- then n_tq tail-prediction queries
+// score_fn(tq_heads[i], e, tq_rels[i]) with true candidate tq_true[i].  Outputs hold the head queries first.
+extern "C" int blp_rank_queries(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                const float *hq_tails, const float *hq_rels, const int64_t *hq_true, int64_t n_hq,
+                                const float *tq_heads, const float *tq_rels, const int64_t *tq_true, int64_t n_tq,
+                                int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                                float *recip, uint8_t *hits, double *sums, void *workspace, void *stream) {
+    reset_launch_count();
+    const int64_t nq = n_hq + n_tq;
+    if (n_hq < 0 || n_tq < 0) { set_error("negative size"); return BLP_EINVAL; }
+    int rc = check_rank_args(model, d, nq, n_local, ent, nullptr, nullptr, gt, ge, nullptr, nullptr, true_score);
+    if (rc) return rc;
+    if (nq == 0) return BLP_OK;
+    if (n_local <= 0) { set_error("blp_rank_queries gathers the true rows from the table: empty shard"); return BLP_EINVAL; }
+    if ((n_hq > 0 && (!hq_tails || !hq_rels || !hq_true)) || (n_tq > 0 && (!tq_heads || !tq_rels || !tq_true))) {
+        set_error("null pointer argument");
+        return BLP_EINVAL;
+    }
+    StepOut o{};
+    if ((rc = fill_kvalues(o.kv, k_values_host, nk))) return rc;
+    o.recip = recip; o.hits = hits; o.sums = sums; o.workspace = workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RowRef hq_h = RowRef{ent, (const long long *)hq_true, 1, ent_offset, n_local};
+    const RowRef tq_t = RowRef{ent, (const long long *)tq_true, 1, ent_offset, n_local};
+    if (n_hq == n_tq) {
+        RankJob j = make_job(model, ent, n_local, ent_offset, d, hq_h, dense_rows(hq_tails), dense_rows(hq_rels), n_hq, n_hq,
+                             gt, ge, true_score);
+        j.h2 = dense_rows(tq_heads); j.t2 = tq_t; j.r2 = dense_rows(tq_rels); j.split = 1;
+        return rank_step_impl(j, o, st);
+    }
+    // unequal parts: one single-role pass each, metrics over the concatenation afterwards
+    StepOut part = o;
+    part.sums = nullptr; part.recip = nullptr; part.hits = nullptr;
+    if (n_hq > 0) {
+        RankJob j = make_job(model, ent, n_local, ent_offset, d, hq_h, dense_rows(hq_tails), dense_rows(hq_rels), n_hq, n_hq,
+                             gt, ge, true_score);
+        j.roles = 1;
+        if ((rc = rank_step_impl(j, part, st))) return rc;
+    }
+    if (n_tq > 0) {
+        RankJob j = make_job(model, ent, n_local, ent_offset, d, dense_rows(tq_heads), tq_t, dense_rows(tq_rels), n_tq, n_tq,
+                             gt + n_hq, ge + n_hq, true_score + n_hq);
+        j.roles = 2;
+        if ((rc = rank_step_impl(j, part, st))) return rc;
+    }
+    if (sums) {
+        metrics_reduce_kernel<<<1, 1024, 0, st>>>(gt, ge, nq, o.kv, recip, hits, sums);
+        count_launch();
+        BLP_CUDA(cudaGetLastError());
+    }
+    return BLP_OK;
+}
+
+namespace blp { void set_debug_timestamp_buffer(unsigned long long *p); }
+extern "C" int blp_debug_timestamps(void *buffer) {
+    blp::set_debug_timestamp_buffer(reinterpret_cast<unsigned long long *>(buffer));
+    return BLP_OK;
 }
 
 extern "C" int64_t blp_fast_table_bytes(int64_t n_local) { return fast_table_ws_bytes(n_local); }
@@ -424,18 +665,16 @@ extern "C" int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local,
     if (d != kD) { set_error("fast mode is specialised for d = %d (got %d)", kD, d); return BLP_EDIM; }
     if (model == BLP_MODEL_TRANSE) { set_error("fast (tensor-core) mode covers distmult / complex / simple only"); return BLP_EINVAL; }
     if (t == 0) return BLP_OK;
-    if (!rel_weight || !triples || num_rel <= 0 || !table_ws || !query_ws) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if (!table_ws || !query_ws) { set_error("null pointer argument"); return BLP_EINVAL; }
+    if ((rc = check_sweep_args(rel_weight, num_rel, triples, t, h_rows, t_rows, tail_off, n_local))) return rc;
     if (!aligned16(table_ws) || !aligned16(query_ws)) { set_error("workspaces must be 16-byte aligned"); return BLP_EINVAL; }
-    if ((h_rows == nullptr) != (t_rows == nullptr)) { set_error("h_rows and t_rows must both be given or both NULL"); return BLP_EINVAL; }
-    if (tail_off < t) { set_error("tail_off must be >= t"); return BLP_EINVAL; }
     if (scores_out && ld_scores < n_local) { set_error("ld_scores must be >= n_local"); return BLP_EINVAL; }
-    const long long *tr = (const long long *)triples;
-    const RowRef h = h_rows ? dense_rows(h_rows) : RowRef{ent, tr + 0, 3, ent_offset, n_local};
-    const RowRef tt = t_rows ? dense_rows(t_rows) : RowRef{ent, tr + 1, 3, ent_offset, n_local};
-    const RowRef r = RowRef{rel_weight, tr + 2, 3, 0, num_rel};
-    if (!h_rows && n_local == 0) { set_error("cannot gather query rows from an empty shard; pass h_rows / t_rows"); return BLP_EINVAL; }
-    return rank_impl(model, ent, n_local, ent_offset, d, h, tt, r, t, tail_off, filt_indptr, filt_idx, gt, ge, gt_f, ge_f,
-                     true_score, (cudaStream_t)stream, tr, table_ws, query_ws, scores_out, ld_scores);
+    const TripleRows q = triple_rows(ent, n_local, ent_offset, rel_weight, num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(model, ent, n_local, ent_offset, d, q.h, q.t, q.r, t, tail_off, gt, ge, true_score);
+    j.filt_indptr = (const long long *)filt_indptr; j.filt_idx = (const long long *)filt_idx; j.gt_f = gt_f; j.ge_f = ge_f;
+    j.triples = (const long long *)triples; j.fast_table_ws = table_ws; j.fast_query_ws = query_ws; j.fast_scores = scores_out;
+    j.fast_ld = ld_scores;
+    return rank_impl(j, (cudaStream_t)stream);
 }
 
 extern "C" int blp_score_bcast(int model, const float *heads, int64_t hsA, int64_t hsC, const float *tails,
@@ -458,6 +697,7 @@ extern "C" int blp_score_bcast(int model, const float *heads, int64_t hsA, int64
         // the unused query operand aliases a valid row block so the TMA staging reads defined memory
         a.h = dense_rows(cand_h ? tails : heads); a.t = dense_rows(cand_h ? tails : heads); a.r = dense_rows(rels);
         a.b = A; a.tail_off = A; a.true_score = nullptr; a.gt = nullptr; a.ge = nullptr; a.scores_out = out; a.ld_scores = C;
+        a.h2 = a.h; a.t2 = a.t; a.r2 = a.r; a.split_sets = 0; a.force_cfg = -1;
         a.roles = cand_h ? 1 : 2; a.groups = 0; a.use_tma = sweep_env_use_tma(); a.negzero2 = kNegZero2;
         return launch_sweep_dyn(model, a, st);
     }

@@ -30,7 +30,10 @@
 // The kernel is FP32-pipe bound for full groups (2-3 lane-ops per (query, candidate, dim) against 4/Q
 // bytes) and HBM bound for the small-batch shapes; see DESIGN.md.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "blp_sweep.h"
 
@@ -70,7 +73,12 @@ struct TileLayout {
 
 template <int MODEL, class C>
 struct Stages {
-    static constexpr int ST = (C::QV_BYTES + 3 * TileLayout<MODEL>::kFloats * 4 <= kSmemBudget) ? 3 : 2;   // tile buffers
+    // per query: 128 term floats (in-kernel true scores) + three row pointers + flags
+    static constexpr int kPerWarp = (C::NQ + kCW - 1) / kCW;                // queries per warp (ql = warp + kCW * u)
+    static constexpr int kRound = kPerWarp < 4 ? kPerWarp : 4;               // queries per warp and round
+    static constexpr int kTermRows = kCW * kRound;
+    static constexpr int kPrologueBytes = kTermRows * kD * 4 + C::NQ * (3 * 8 + 3 * 4 + 4);
+    static constexpr int ST = (C::QV_BYTES + kPrologueBytes + 3 * TileLayout<MODEL>::kFloats * 4 <= kSmemBudget) ? 3 : 2;   // tile buffers
 };
 
 template <int MODEL, class C>
@@ -78,6 +86,9 @@ struct __align__(1024) SweepSmem {
     static constexpr int ST = Stages<MODEL, C>::ST;
     float ctile[ST][TileLayout<MODEL>::kFloats];   // candidate tiles (1024-byte aligned for the TMA swizzle)
     float qv[C::NS * C::TQP][2][kD][2];       // [query pair][operand vector][position][half], processing order
+    float tm[Stages<MODEL, C>::kTermRows][kD];   // per-position terms of the true-triple scores: 4 queries per warp and round
+    const float *rowp[C::NQ][3];              // h / t / r row of every query of the current group
+    int rowok[C::NQ][3];                      // index inside its table (h / t / r)
     float st[C::NQ];                          // true-triple scores of the current group's queries
     uint64_t full_bar[ST];
     uint64_t empty_bar[ST];
@@ -149,6 +160,59 @@ __device__ __forceinline__ void fold_query(const float *__restrict__ h, const fl
             }
         }
     }
+}
+
+// The same folding from values already in registers: h0 = h[j], t0 = t[j], r0 = r[j]; for the halves models j < 64 and
+// h1 = h[64 + j], t1 = t[64 + j], r1 = r[64 + j].
+template <int MODEL, bool HEAD_PRED>
+__device__ __forceinline__ void fold_vals(float h0, float t0, float r0, float h1, float t1, float r1, int j,
+                                          float *__restrict__ qp) {
+    const int p = perm_pos<MODEL>(j);
+    auto put = [&](int v, int pos, float x) { qp[(v * kD + pos) * 2] = x; };
+    if (MODEL == BLP_MODEL_TRANSE || MODEL == BLP_MODEL_DISTMULT) {
+        if (HEAD_PRED) {
+            put(0, p, r0);
+            put(1, p, t0);
+        } else {
+            put(0, p, (MODEL == BLP_MODEL_TRANSE) ? fadd(h0, r0) : fmul(h0, r0));
+            put(1, p, 0.0f);
+        }
+    } else if (MODEL == BLP_MODEL_COMPLEX) {
+        if (HEAD_PRED) {                 // v0 = (rr | ri), v1 = (tr | ti)
+            put(0, p, r0); put(0, 64 + p, r1);
+            put(1, p, t0); put(1, 64 + p, t1);
+        } else {
+            put(0, p, fmul(r0, h0));        // A
+            put(0, 64 + p, fmul(r0, h1));   // B
+            put(1, p, fmul(r1, h0));        // C
+            put(1, 64 + p, fmul(r1, h1));   // D
+        }
+    } else {  // SIMPLE
+        if (HEAD_PRED) {                 // candidate = (hh, ht)
+            put(0, p, r0);                            // ra
+            put(0, 64 + p, t1);                       // tt
+            put(1, p, fmul(t0, r1));                  // th * rb
+            put(1, 64 + p, 0.0f);
+        } else {                         // candidate = (th, tt)
+            put(0, p, fmul(h0, r0));                  // hh * ra
+            put(0, 64 + p, r1);                       // rb
+            put(1, p, h1);                            // ht
+            put(1, 64 + p, 0.0f);
+        }
+    }
+}
+
+// one per-position term of the true-triple score, operation order of models.py:222-248
+template <int MODEL>
+__device__ __forceinline__ float true_term(float h0, float t0, float r0, float h1, float t1, float r1) {
+    if (MODEL == BLP_MODEL_TRANSE) return fabsf(fsub(fadd(h0, r0), t0));
+    if (MODEL == BLP_MODEL_DISTMULT) return fmul(fmul(h0, r0), t0);
+    if (MODEL == BLP_MODEL_COMPLEX) {        // (hr, hi) = (h0, h1), (tr, ti) = (t0, t1), (rr, ri) = (r0, r1)
+        float p = fadd(fmul(fmul(r0, h0), t0), fmul(fmul(r0, h1), t1));
+        p = fadd(p, fmul(fmul(r1, h0), t1));
+        return fsub(p, fmul(fmul(r1, h1), t0));
+    }
+    return fadd(fmul(fmul(h0, r0), t1), fmul(fmul(t0, r1), h1));   // SimplE: hh ra tt + th rb ht
 }
 
 // ---- per-position arithmetic on query PAIRS (f2 = two queries, same candidate) ----
@@ -361,6 +425,16 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
 }
 #undef HEAD_PRED
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define BLP_TS(slot)                                                                                  \
+    do {                                                                                              \
+        if (args.dbg && tid == 0) args.dbg[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();      \
+    } while (0)
+
 __device__ __forceinline__ void consumer_bar_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory");
 }
@@ -399,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
     // 1024-byte alignment for the TMA swizzle; plain pointer arithmetic keeps the shared address space (LDS, not LD)
     SM &sm = *reinterpret_cast<SM *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    BLP_TS(0);
 
     if (tid == 0) {
         for (int s = 0; s < SM::ST; ++s) {
@@ -474,35 +549,137 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 
     int it = 0;
     long long id = id_begin;
+    BLP_TS(1);
+    int nseg = 0;
     while (id < id_end) {
+        ++nseg;
         // ---- segment = the run of this CTA's tiles that belong to one triple group
         const long long grp = id / ntiles;
         const long long seg_end = min(id_end, (grp + 1) * ntiles);
         const long long t0 = grp * QM::kTriplesPerGroup;                   // first triple of this group
 
         consumer_bar_sync();                      // everyone is done with the previous group's vectors
-        for (int idx = tid; idx < C::NQ * kD; idx += kCW * 32) {
-            const int ql = idx >> 7, j = idx & (kD - 1);                   // ql = slot * SQ + query in slot
+        // (1) the h / t / r row of every query of this group, resolved once (one round of index loads)
+        if (tid < C::NQ * 3) {
+            const int ql = tid / 3, which = tid - 3 * ql;
             const int s_ = ql / C::SQ, qi = ql % C::SQ;
-            const bool hp = QM::is_head(s_, qi);
+            const bool hq = QM::is_head(s_, qi);
             const long long tr = t0 + QM::triple(s_, qi);
-            float *qp = &sm.qv[ql >> 1][0][0][ql & 1];
-            if (tr < args.b) {
-                const float *h = args.h.row(tr, kD), *t = args.t.row(tr, kD), *r = args.r.row(tr, kD);
-                if (hp) fold_query<MODEL, true>(h, t, r, j, qp);
-                else fold_query<MODEL, false>(h, t, r, j, qp);
-            } else {
-                qp[j * 2] = 0.0f;
-                qp[(kD + j) * 2] = 0.0f;
-            }
+            const long long trc = tr < args.b ? tr : args.b - 1;
+            const RowRef &X = which == 0 ? (hq ? args.h : args.h2) : which == 1 ? (hq ? args.t : args.t2) : (hq ? args.r : args.r2);
+            sm.rowp[ql][which] = X.row(trc, kD);
+            sm.rowok[ql][which] = X.in_range(trc) ? 1 : 0;
         }
-        if (tid < C::NQ) {
+        consumer_bar_sync();
+        // (2) one warp per query row, one 16-byte chunk per lane: the rows are read once; the folded operands go to
+        // their place, the per-position terms of the true-triple score are parked for the summation chains.
+        // (3) the reference's summation order, the chains of 4 queries side by side in the warp's lanes: lane u runs
+        // the 128 dependent adds of torch.norm(p=1) for the round's u-th query; for torch.sum, lanes 8u .. 8u+7 run
+        // ATen's 8-lane x 4-accumulator cascade of the u-th query.
+        constexpr bool kHalves = MODEL == BLP_MODEL_COMPLEX || MODEL == BLP_MODEL_SIMPLE;
+        constexpr int kPerWarp = (C::NQ + kCW - 1) / kCW;              // this warp's queries: ql = warp + kCW * u
+        constexpr int kTermRows = Stages<MODEL, C>::kTermRows;
+        constexpr int L = kHalves ? kD / 2 : kD;
+        const int tm0 = warp * Stages<MODEL, C>::kRound;                // this warp's term rows
+#pragma unroll 1
+        for (int u0 = 0; u0 < kPerWarp; u0 += 4) {
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int ql = warp + kCW * (u0 + uu);
+                if (u0 + uu >= kPerWarp || ql >= C::NQ) continue;     // warp-uniform
+                const int s_ = ql / C::SQ, qi = ql % C::SQ;
+                const bool hp = QM::is_head(s_, qi);
+                const long long tr = t0 + QM::triple(s_, qi);
+                float *qp = &sm.qv[ql >> 1][0][0][ql & 1];
+                const int c = kHalves ? (lane & 15) : lane;
+                if (tr < args.b) {
+                    const float *h = sm.rowp[ql][0], *t = sm.rowp[ql][1], *r = sm.rowp[ql][2];
+                    const float4 h0 = __ldg(reinterpret_cast<const float4 *>(h) + c), t0v = __ldg(reinterpret_cast<const float4 *>(t) + c),
+                                 r0 = __ldg(reinterpret_cast<const float4 *>(r) + c);
+                    float4 h1 = h0, t1 = t0v, r1 = r0;
+                    if (kHalves) {
+                        h1 = __ldg(reinterpret_cast<const float4 *>(h + 64) + c);
+                        t1 = __ldg(reinterpret_cast<const float4 *>(t + 64) + c);
+                        r1 = __ldg(reinterpret_cast<const float4 *>(r + 64) + c);
+                    }
+                    if (!kHalves || lane < 16) {
+                        const float ha[4] = {h0.x, h0.y, h0.z, h0.w}, ta[4] = {t0v.x, t0v.y, t0v.z, t0v.w}, ra[4] = {r0.x, r0.y, r0.z, r0.w};
+                        const float hb[4] = {h1.x, h1.y, h1.z, h1.w}, tb[4] = {t1.x, t1.y, t1.z, t1.w}, rb[4] = {r1.x, r1.y, r1.z, r1.w};
+                        float o[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (hp) fold_vals<MODEL, true>(ha[k], ta[k], ra[k], hb[k], tb[k], rb[k], 4 * c + k, qp);
+                            else fold_vals<MODEL, false>(ha[k], ta[k], ra[k], hb[k], tb[k], rb[k], 4 * c + k, qp);
+                            o[k] = true_term<MODEL>(ha[k], ta[k], ra[k], hb[k], tb[k], rb[k]);
+                        }
+                        if (args.fuse_true) *reinterpret_cast<float4 *>(&sm.tm[tm0 + uu][4 * c]) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                } else if (!kHalves || lane < 16) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = 4 * c + k;
+                        qp[j * 2] = 0.0f;
+                        qp[(kD + j) * 2] = 0.0f;
+                        if (kHalves) {
+                            qp[(64 + j) * 2] = 0.0f;
+                            qp[(kD + 64 + j) * 2] = 0.0f;
+                        }
+                    }
+                }
+            }
+            if (!args.fuse_true) continue;
+            __syncwarp();
+            float sv = 0.0f;
+            int uu_mine = -1;                                          // the chain this lane finishes
+            if (MODEL == BLP_MODEL_TRANSE) {
+                if (lane < 4) {
+                    const float *tu = &sm.tm[tm0 + (lane < Stages<MODEL, C>::kRound ? lane : 0)][0];
+#pragma unroll 8
+                    for (int j = 0; j < kD; j += 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(tu + j);
+                        sv = fadd(fadd(fadd(fadd(sv, v.x), v.y), v.z), v.w);
+                    }
+                    sv = -sv;
+                    uu_mine = lane;
+                }
+            } else {
+                const int uu = lane >> 3, l = lane & 7;
+                const float *tu = &sm.tm[tm0 + (uu < Stages<MODEL, C>::kRound ? uu : 0)][0];
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < L / 32; ++k)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) acc[a] = fadd(acc[a], tu[32 * k + 8 * a + l]);
+                const float cl = fadd(fadd(fadd(acc[0], acc[1]), acc[2]), acc[3]);
+#pragma unroll
+                for (int ll = 0; ll < 8; ++ll) sv = fadd(sv, __shfl_sync(0xffffffffu, cl, (lane & 24) + ll));
+                if (MODEL == BLP_MODEL_SIMPLE) sv = fmul(sv, 0.5f);
+                if (l == 0) uu_mine = uu;
+            }
+            if (uu_mine >= 0) {
+                const int ql = warp + kCW * (u0 + uu_mine);
+                if (u0 + uu_mine < kPerWarp && ql < C::NQ) {
+                    const int s_ = ql / C::SQ, qi = ql % C::SQ;
+                    const long long tr = t0 + QM::triple(s_, qi);
+                    // an index outside the table (train.py:137-138 asserts this never happens): NaN compares false
+                    // against every candidate, so the query reports gt = ge = 0 and is detectable
+                    const float v = (sm.rowok[ql][0] & sm.rowok[ql][1] & sm.rowok[ql][2]) ? sv : __int_as_float(0x7fc00000);
+                    sm.st[ql] = tr < args.b ? v : 0.0f;
+                    if (tr < args.b && id == grp * ntiles && args.true_score_out)
+                        args.true_score_out[(QM::is_head(s_, qi) ? 0 : tail_base) + tr] = v;
+                }
+            }
+            __syncwarp();
+        }
+        if (!args.fuse_true && tid < C::NQ) {
             const int s_ = tid / C::SQ, qi = tid % C::SQ;
             const long long tr = t0 + QM::triple(s_, qi);
             const long long qo = (QM::is_head(s_, qi) ? 0 : tail_base) + tr;
             sm.st[tid] = (args.true_score && tr < args.b) ? args.true_score[qo] : 0.0f;
         }
+        if (nseg == 1) BLP_TS(2);
         consumer_bar_sync();
+        if (nseg == 1) BLP_TS(3);
 
         float st[C::SQ];
         long long qo[C::SQ];                      // output row of each of this thread's queries, -1 = padding
@@ -534,6 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             const int buf = it % SM::ST;
             const uint32_t use = (uint32_t)(it / SM::ST);
             mbar_wait(&sm.full_bar[buf], use & 1u);
+            if (it == 0) BLP_TS(4);
             float s[C::SQ][C::TC];
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
@@ -594,13 +772,91 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             }
         }
     }
+
+    BLP_TS(5);
+    if (args.dbg && tid == 0) { args.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)nseg; args.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)(id_end - id_begin); }
+    if (!args.fuse_epilogue) return;
+    // ---- fused epilogue: the last CTA to finish turns the accumulated counters into the step's results
+    // (utils.py:103-109, train.py:154-157) and leaves the workspace zeroed for the next call
+    // scratch in the (now idle) query-operand / true-score areas of the dynamic shared memory
+    volatile int *s_last = reinterpret_cast<volatile int *>(&sm.st[0]);
+    double (*s_red)[9] = reinterpret_cast<double (*)[9]>(&sm.qv[0][0][0][0]);
+    consumer_bar_sync();                      // this CTA's counter updates are issued (CTA-scope order) ...
+    if (tid == 0) {
+        __threadfence();                      // ... and made visible device-wide before the ticket (cumulative fence)
+        const unsigned int done = atomicAdd(args.ticket, 1u);
+        *s_last = (done == gridDim.x - 1) ? 1 : 0;
+    }
+    consumer_bar_sync();
+    BLP_TS(6);
+    if (!*s_last) return;
+    __threadfence();
+    double acc[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+    for (long long i = tid; i < args.out_len; i += kCW * 32) {
+        const bool live = i < args.b || i >= args.tail_off;       // [b, tail_off) is a gap when the outputs are slices
+        if (!live) continue;
+        const int g = __ldcg(args.gt + i), e = __ldcg(args.ge + i);
+        args.gt[i] = 0;
+        args.ge[i] = 0;
+        args.gt_out[i] = g;
+        args.ge_out[i] = e;
+        const float avg = fmul((float)((long long)g + 1 + (long long)e), 0.5f);
+        const float rr = __frcp_rn(avg);
+        if (args.recip) args.recip[i] = rr;
+        acc[0] += (double)rr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < args.kv.nk) {
+                const bool hit = avg <= (float)args.kv.k[j];
+                if (hit) acc[1 + j] += 1.0;
+                if (args.hits) args.hits[i * args.kv.nk + j] = hit;
+            }
+    }
+    if (args.sums) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            if (lane == 0) s_red[warp][j] = acc[j];
+        }
+        consumer_bar_sync();
+        if (tid <= args.kv.nk) {
+            double tot = 0.0;
+            for (int w = 0; w < kCW; ++w) tot += s_red[w][tid];
+            args.sums[tid] = tot;
+        }
+    }
+    if (tid == 0) *args.ticket = 0u;
+    BLP_TS(7);
 }
 
 // ---- host side ----------------------------------------------------------------
+unsigned long long *debug_timestamp_buffer();
+static unsigned long long *tl_dbg_get() { return debug_timestamp_buffer(); }
+// Per-launch host work is kept to the launch itself (it is a large share of a 20 us eval batch): the SM count and
+// the shared-memory opt-in are cached per device, the tensor map per (table pointer, rows) in a small thread-local
+// cache, the tuning environment variables are read once.
+constexpr int kMaxDevices = 64;
+
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 static int num_sms() {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
+    static std::atomic<int> cached[kMaxDevices];
+    const int dev = current_device();
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
@@ -619,24 +875,41 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 2-D view of the table shard: [n_local rows][128 floats], boxes of [128 rows][32 floats], 128-byte swizzle
+// 2-D view of the table shard: [n_local rows][128 floats], boxes of [128 rows][32 floats], 128-byte swizzle.
+// The descriptor depends only on (pointer, rows), so a handful of them are remembered per host thread.
 static bool make_table_tmap(CUtensorMap *tm, const float *ent, long long n_local) {
+    struct Entry { const float *ent; long long n; CUtensorMap map; };
+    constexpr int kSlots = 8;
+    static thread_local Entry cache[kSlots];
+    static thread_local int next = 0;
+    for (int i = 0; i < kSlots; ++i)
+        if (cache[i].ent == ent && cache[i].n == n_local) { *tm = cache[i].map; return true; }
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)n_local};
     const cuuint64_t strides[1] = {(cuuint64_t)kD * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t)kCT};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ent), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ent), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    cache[next] = Entry{ent, n_local, *tm};
+    next = (next + 1) % kSlots;
+    return true;
 }
 
 template <int MODEL, class C, int ROLES>
 static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     const size_t smem = sizeof(SweepSmem<MODEL, C>) + 1024;
-    BLP_CUDA(cudaFuncSetAttribute(sweep_kernel<MODEL, C, ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::atomic<unsigned long long> attr_done{0};        // bit per device: opt-in to > 48 KB dynamic smem
+    const int dev = current_device();
+    if (!((attr_done.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+        BLP_CUDA(cudaFuncSetAttribute(sweep_kernel<MODEL, C, ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done.fetch_or(1ull << dev, std::memory_order_relaxed);
+    }
     SweepArgs args = a;
+    args.dbg = tl_dbg_get();
     const int tg = QueryMap<C, ROLES>::kTriplesPerGroup;
     args.groups = (a.b + tg - 1) / tg;
     const long long ntiles = (a.n_local + kCT - 1) / kCT;
@@ -645,8 +918,10 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     const long long sms = num_sms();
     const unsigned grid = (unsigned)(items < sms ? items : sms);
     CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if (MODEL == BLP_MODEL_TRANSE && args.use_tma && !make_table_tmap(&tmap, a.ent, a.n_local)) args.use_tma = 0;
+    if (MODEL == BLP_MODEL_TRANSE && args.use_tma) {
+        if (!make_table_tmap(&tmap, a.ent, a.n_local)) args.use_tma = 0;
+    }
+    if (!(MODEL == BLP_MODEL_TRANSE && args.use_tma)) memset(&tmap, 0, sizeof(tmap));
     prof_begin(1, st);
     sweep_kernel<MODEL, C, ROLES><<<grid, kThreads, smem, st>>>(args, tmap);
     prof_end(1, st);
@@ -655,18 +930,26 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     return BLP_OK;
 }
 
+static int env_sweep_cfg() {
+    static const int v = []() {
+        const char *e = getenv("BLP_SWEEP_CFG");       // tuning aid: force one register tile
+        return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
+    }();
+    return v;
+}
+
 // Register-tile shape by batch size: the smallest slot that holds the batch without padding queries.
-// BLP_SWEEP_CFG=0..4 forces one (tuning aid).
+// a.force_cfg (or BLP_SWEEP_CFG=0..4) forces one: 2 / 4 / 8 / 16 / 32 triples per table pass.
 template <int MODEL>
 static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
-    if (a.roles == 1) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 1>(a, st);   // score_fn fast path: full tiles only
+    if (a.roles == 1) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 1>(a, st);   // single role: full tiles only
     if (a.roles == 2) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 2>(a, st);
     // up to 256 triples the 16-triple groups of Cfg<4,2> give twice as many (group, tile) work items, which evens out
     // the per-CTA shares (E = 64: 44 vs 50 us, E = 256: 110 vs 124 us); beyond that the larger register tile of
     // Cfg<4,4> and its shared-relation path win (E = 1024 in relation order: 0.321 vs 0.390 ms)
     int cfg = a.b <= 2 ? 0 : a.b <= 4 ? 1 : a.b <= 8 ? 2 : a.b <= 256 ? 3 : 4;
-    const char *e = getenv("BLP_SWEEP_CFG");
-    if (e && e[0] >= '0' && e[0] <= '4') cfg = e[0] - '0';
+    if (a.force_cfg >= 0 && a.force_cfg <= 4) cfg = a.force_cfg;
+    else if (env_sweep_cfg() >= 0) cfg = env_sweep_cfg();
     switch (cfg) {
     case 0: return launch_sweep_cfg<MODEL, Cfg<1, 1>, 3>(a, st);             //  2 triples / group (split roles)
     case 1: return launch_sweep_cfg<MODEL, Cfg<2, 1>, 3>(a, st);             //  4
@@ -685,10 +968,22 @@ int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st) {
     }
 }
 
+// Cfg index whose group holds `group_triples` triples (the reference's eval batch as a table-pass size), -1 = auto
+int sweep_cfg_for_group(long long group_triples) {
+    if (group_triples <= 0) return -1;
+    return group_triples <= 2 ? 0 : group_triples <= 4 ? 1 : group_triples <= 8 ? 2 : group_triples <= 16 ? 3 : 4;
+}
+
+static thread_local unsigned long long *tl_dbg = nullptr;
+unsigned long long *debug_timestamp_buffer() { return tl_dbg; }
+void set_debug_timestamp_buffer(unsigned long long *p) { tl_dbg = p; }
+
 int sweep_env_use_tma() {
-    const char *e = getenv("BLP_EVAL_PRODUCER");
-    if (e && (e[0] == 'l' || e[0] == 'L')) return 0;   // "ldg"
-    return 1;
+    static const int v = []() {
+        const char *e = getenv("BLP_EVAL_PRODUCER");
+        return (e && (e[0] == 'l' || e[0] == 'L')) ? 0 : 1;   // "ldg"
+    }();
+    return v;
 }
 
 }  // namespace blp

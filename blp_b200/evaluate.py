@@ -14,6 +14,7 @@ size.  The query rows (true head / tail rows) are exchanged once per sweep with
 a bit-preserving all-reduce (every row is owned by exactly one rank).
 """
 import contextlib
+import ctypes
 
 import numpy as np
 import torch
@@ -76,7 +77,7 @@ def gather_rows(ent_shard, ent_offset, idx, group=None):
 
 
 def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, filter_triples=None,
-               filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384,
+               filter_csr=None, k_values=K_VALUES, ent_offset=0, group=None, chunk=16384, group_triples=0,
                h_rows=None, t_rows=None, count_fn=None, mode="exact", fast_table=None, sort_by_relation=True,
                overlap_chunks=True):
     """Rank every test triple against all candidate entities (train.py:128-171 for the whole sweep).
@@ -92,6 +93,9 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 precomputed with the head-prediction queries of ALL T triples first
     ent_offset / group   entity-sharded sweeps: global row id of ent_emb[0] and the process group whose ranks hold the
                 other row blocks (one all-reduce of the counters per sweep); group=None = not sharded
+    group_triples   exact mode, D = 128: triples per pass over the table (0 = chosen from T; 2 / 4 / 8 / 16 / 32 forces
+                it).  This is what the reference's `eval_batch_size` controls -- every batch streams the whole table
+                once -- so `group_triples=2` reproduces the Wikidata5M setting (HBM-bound) in ONE launch for all T
     h_rows / t_rows   optional pre-gathered (T, D) true head / tail rows (replicated)
     mode        "exact" (default): every score carries the reference's fp32 roundings, ranks are bit-exact;
                 "fast": distmult / complex / simple at D = 128 as a split-FP16 tensor-core contraction
@@ -163,14 +167,28 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
         outs = {name: counters[i] for i, name in enumerate(names)}
         outs["true_score"] = true_score
-        # a sweep cut into several chunks (the reference's eval batches): all true scores in one launch up front,
-        # then one sweep launch per chunk
-        split = mode == "exact" and T > chunk
+        fused_metrics = None
+        # exact mode without host-side filter lists: ONE launch for the whole sweep (true scores per query group inside
+        # the sweep kernel; on a single GPU without filters the same launch also produces the metrics)
+        one_step = mode == "exact" and (not filtered or dev_index is not None) and ent_emb.shape[0] > 0
+        if one_step:
+            if world == 1 and not filtered and perm is None:
+                fused_metrics = ops.alloc_metrics(dev, 2 * T, k_values.numel() if torch.is_tensor(k_values) else len(k_values))
+            launches += ops.rank_step(rel_model, ent_emb, rel_weight.detach(), triples, outs, h_rows, t_rows, ent_offset,
+                                      group_triples, k_values, fused_metrics)
+            if dev_index is not None:
+                # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
+                launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, 0, T,
+                                               dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
+                                               h_rows, t_rows, ent_offset)
+        # legacy chunked path (tensor-core mode, host-built CSR filter lists): all true scores in one launch up
+        # front, then one sweep launch per chunk
+        split = mode == "exact" and T > chunk and not one_step
         if split:
             launches += ops.true_scores(rel_model, ent_emb, rel_weight.detach(), triples, outs, h_rows, t_rows, ent_offset)
         # consecutive chunks are independent (disjoint output slots, read-only table), so they alternate between two
         # side streams: the launch / fold / pipeline-fill head of one chunk's kernel overlaps the tail of the previous
-        # one (8 of 55 us per batch on a 600,000-row shard at eval batch 2).  Fork / join with events, capture-safe.
+        # one.  Fork / join with events, capture-safe.
         n_chunks = (T + chunk - 1) // chunk if T else 0
         lanes = None
         if overlap_chunks and split and n_chunks >= 4:
@@ -180,7 +198,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             fork.record(main)
             for s_ in lanes:
                 s_.wait_event(fork)
-        for ci, lo in enumerate(range(0, T, chunk)):
+        for ci, lo in enumerate(range(0, T, chunk) if not one_step else ()):
             hi = min(T, lo + chunk)
             ctx = torch.cuda.stream(lanes[ci & 1]) if lanes is not None else contextlib.nullcontext()
             with ctx:
@@ -190,7 +208,6 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                                                  None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
                                                  fast_table_ws=fast_table if mode == "fast" else None, counts_only=split)
                 if dev_index is not None:
-                    # filtered ranks as a sparse correction from the device-resident index: no per-batch host work
                     launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
                                                    dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
                                                    None if h_rows is None else h_rows[lo:hi],
@@ -206,6 +223,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
             counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
     else:
         # test seam: the sharding / collective logic with a CPU stand-in for blp_eval_rank
+        fused_metrics = None
         heads, tails, rels = triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous()
         if h_rows is None:
             h_rows = gather_rows(ent_emb, ent_offset, heads, group)
@@ -232,7 +250,10 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     out = {name: counters[i] for i, name in enumerate(names)}
     out["true_score"] = true_score
     out["launches"] = launches
-    if count_fn is None:
+    if fused_metrics is not None:
+        out["recip"], out["hits"], out["sums"] = (fused_metrics["recip"], fused_metrics["hits"].view(torch.bool),
+                                                  fused_metrics["sums"])
+    elif count_fn is None:
         for suffix in ("", "_f") if filtered else ("",):
             recip, hits, sums = ops.rank_metrics(out["gt" + suffix], out["ge" + suffix], k_values)
             out["recip" + suffix], out["hits" + suffix], out["sums" + suffix] = recip, hits, sums
@@ -244,17 +265,19 @@ class RankSweepPlan:
     """`rank_sweep` for repeated calls on the same table with a fixed number of test triples.
 
     Everything that does not depend on the triples is done once: argument validation, output / scratch
-    allocation, the ctypes argument lists.  A call is then two or three C-ABI launches (blp_rank_sweep[_fast],
-    blp_filter_correct, blp_rank_metrics) and ~15 us of host time instead of ~65 us, which matters for the
-    reference's small eval batches (64 triples, train.py:128) and for the tensor-core mode, whose GPU time per
-    batch is of the same order.  The returned tensors are STATIC: the next call overwrites them.
+    allocation, and -- exact mode -- the C-side plan object (blp_plan_create) that holds every static argument, so a
+    call is ONE ctypes call with three arguments and ONE kernel launch (blp_plan_run: true scores, sweep and metrics
+    fused).  That matters for the reference's small eval batches (64 triples, train.py:128), where host time and
+    launch count are the cost.  With a filter index the correction and the two metric reductions are separate
+    launches; the tensor-core mode keeps its fold + sweep + metrics launches.  The returned tensors are STATIC: the
+    next call overwrites them.
 
-        plan = blp_b200.RankSweepPlan("distmult", ent_emb, model.rel_emb.weight, num_triples=64, mode="fast")
+        plan = blp_b200.RankSweepPlan("transe", ent_emb, model.rel_emb.weight, num_triples=64)
         for triples in loader: out = plan(rows)      # out["sums"], out["gt"], ... as rank_sweep
     """
 
     def __init__(self, rel_model, ent_emb, rel_weight, num_triples, *, mode="exact", filter_index=None,
-                 k_values=K_VALUES, ent_offset=0, group=None, fast_table=None):
+                 k_values=K_VALUES, ent_offset=0, group=None, fast_table=None, group_triples=0):
         lib = ops.lib()
         self.model_id = ops.model_id(rel_model)
         dev = ops._require_cuda(ent_emb, rel_weight)
@@ -273,6 +296,7 @@ class RankSweepPlan:
         self.filtered = filter_index is not None
         self.filter_index = filter_index
         names = ("gt", "ge", "gt_f", "ge_f") if self.filtered else ("gt", "ge")
+        self._plan = None
         with ops._guard(dev):
             ops._enter(dev)
             buf = torch.empty((len(names) + 1, 2, T), dtype=torch.int32, device=dev)
@@ -284,7 +308,7 @@ class RankSweepPlan:
             for suffix in ("", "_f") if self.filtered else ("",):
                 self.out["recip" + suffix] = torch.empty((2 * T, 1), dtype=torch.float32, device=dev)
                 self.out["hits" + suffix] = torch.empty((2 * T, len(ks)), dtype=torch.uint8, device=dev)
-                self.out["sums" + suffix] = torch.empty(1 + len(ks), dtype=torch.float64, device=dev)
+                self.out["sums" + suffix] = torch.zeros(1 + len(ks), dtype=torch.float64, device=dev)
             self.fast_table = None
             self._qws = None
             if mode == "fast":
@@ -292,16 +316,37 @@ class RankSweepPlan:
                 self._qws = torch.empty(int(lib.blp_fast_query_bytes(T)), dtype=torch.uint8, device=dev)
         p = ops._ptr
         o = self.out
-        # blp_rank_sweep(model, ent, n, off, d, rel, R, TRIPLES, t, H_ROWS, T_ROWS, indptr, idx, tail_off, gt, ge, gt_f, ge_f, ts, ...)
+        # the raw metrics come out of the sweep launch itself on a single GPU (exact mode); sharded sweeps reduce
+        # the counters first, so their metrics stay a separate launch
+        self._fused_metrics = mode == "exact" and self.world == 1
+        if mode == "exact" and T > 0:
+            # private zero-invariant workspace: plans may run on different streams
+            self._ws = torch.zeros(int(lib.blp_rank_step_workspace_bytes(2 * T)), dtype=torch.uint8, device=dev)
+            handle = ctypes.c_void_p()
+            fm = self._fused_metrics
+            ops.check(lib.blp_plan_create(ctypes.byref(handle), self.model_id, p(ent_emb), n, self.ent_offset, d, p(self.rel),
+                                          self.rel.shape[0], T, T, int(group_triples), p(o["gt"]), p(o["ge"]),
+                                          p(o["true_score"]), self._karr, self._nk, p(o["recip"]) if fm else None,
+                                          p(o["hits"]) if fm else None, p(o["sums"]) if fm else None, p(self._ws)),
+                      "blp_plan_create")
+            self._plan = handle
+        # blp_rank_sweep_fast(model, ent, n, off, d, rel, R, TRIPLES, t, H_ROWS, T_ROWS, indptr, idx, tail_off, gt, ge, gt_f, ge_f, ts, ...)
         self._head = (self.model_id, p(ent_emb), n, self.ent_offset, d, p(self.rel), self.rel.shape[0])
         self._tail = (None, None, T, p(o["gt"]), p(o["ge"]), None, None, p(o["true_score"]))
         if mode == "fast":
             self._tail = self._tail + (p(self.fast_table), p(self._qws), None, n)
-        self._sweep_fn = lib.blp_rank_sweep_fast if mode == "fast" else lib.blp_rank_sweep
         self._lib = lib
         for suffix in ("", "_f") if self.filtered else ("",):
             o["hits" + suffix + "_bool"] = o["hits" + suffix].view(torch.bool)
         self.launches = 0
+
+    def __del__(self):
+        plan, self._plan = getattr(self, "_plan", None), None
+        if plan is not None:
+            try:
+                self._lib.blp_plan_destroy(plan)
+            except Exception:       # interpreter shutdown
+                pass
 
     def __call__(self, triples, h_rows=None, t_rows=None):
         T, o, lib = self.T, self.out, self._lib
@@ -315,9 +360,16 @@ class RankSweepPlan:
             h_rows, t_rows = ops._f32c(h_rows), ops._f32c(t_rows)
         with ops._guard(self.dev):
             _, stream = ops._enter(self.dev)
+            launches = 0
+            raw_metrics_done = False
             if T > 0:
-                ops.check(self._sweep_fn(*self._head, triples.data_ptr(), T, ops._ptr(h_rows), ops._ptr(t_rows),
-                                         *self._tail, stream), "blp_rank_sweep")
+                if self._plan is not None:
+                    ops.check(lib.blp_plan_run(self._plan, triples.data_ptr(), ops._ptr(h_rows), ops._ptr(t_rows), stream),
+                              "blp_plan_run")
+                    raw_metrics_done = self._fused_metrics
+                else:
+                    ops.check(lib.blp_rank_sweep_fast(*self._head, triples.data_ptr(), T, ops._ptr(h_rows), ops._ptr(t_rows),
+                                                      *self._tail, stream), "blp_rank_sweep_fast")
                 launches = ops._lib.last_launch_count()
                 if self.filtered:
                     fi = self.filter_index
@@ -326,11 +378,11 @@ class RankSweepPlan:
                                                      ops._ptr(o["true_score"]), ops._ptr(o["gt"]), ops._ptr(o["ge"]),
                                                      ops._ptr(o["gt_f"]), ops._ptr(o["ge_f"]), stream), "blp_filter_correct")
                     launches += 1
-            else:
-                launches = 0
             if self.world > 1:
                 _dist().all_reduce(self.counters, group=self.group)
             for suffix in ("", "_f") if self.filtered else ("",):
+                if suffix == "" and raw_metrics_done:
+                    continue
                 ops.check(lib.blp_rank_metrics(ops._ptr(o["gt" + suffix]), ops._ptr(o["ge" + suffix]), 2 * T, self._karr,
                                                self._nk, ops._ptr(o["recip" + suffix]), ops._ptr(o["hits" + suffix]),
                                                ops._ptr(o["sums" + suffix]), stream), "blp_rank_metrics")

@@ -318,6 +318,117 @@ def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, 
     return _lib.last_launch_count() if b > 0 else 0
 
 
+_step_ws_lock = threading.Lock()
+_step_workspaces = {}
+
+
+def step_workspace(dev, stream_handle, out_len):
+    """Zero-filled scratch of the fused step, one per (device, stream): the kernel leaves it zeroed (blp_b200.h)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, stream_handle)
+    nbytes = int(lib().blp_rank_step_workspace_bytes(int(out_len)))
+    with _step_ws_lock:
+        ws = _step_workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=torch.device("cuda", idx))
+            _step_workspaces[key] = ws
+    return ws
+
+
+def alloc_metrics(dev, out_len, nk):
+    """Output tensors of the in-kernel metrics: recip (out_len, 1) f32, hits (out_len, nk) u8, sums (1 + nk) f64."""
+    return {"recip": torch.empty((out_len, 1), dtype=torch.float32, device=dev),
+            "hits": torch.empty((out_len, nk), dtype=torch.uint8, device=dev),
+            "sums": torch.zeros(1 + nk, dtype=torch.float64, device=dev)}
+
+
+def rank_step(model, ent, rel_weight, triples, out, h_rows=None, t_rows=None, ent_offset=0, group_triples=0,
+              k_values=None, metrics=None):
+    """blp_rank_step over ALL T triples: true scores + sweep (+ metrics) in one launch (d = 128).
+
+    out: contiguous (2, T) tensors gt, ge (int32), true_score (f32); metrics: None, or the dict of
+    `alloc_metrics(dev, 2 * T, nk)` to have utils.get_metrics / the train.py:154-157 sums computed by the same launch.
+    group_triples: triples per table pass (0 = auto; the reference's eval_batch_size, e.g. 2 for Wikidata5M)."""
+    mid = model_id(model)
+    dev = _require_cuda(ent, rel_weight, triples, h_rows, t_rows)
+    if ent.dtype != torch.float32 or not ent.is_contiguous() or ent.dim() != 2:
+        raise ValueError("ent must be a contiguous fp32 (N, D) tensor")
+    rel_weight = _f32c(rel_weight)
+    n, d = ent.shape
+    T = triples.shape[0]
+    if triples.dtype != torch.int64 or not triples.is_contiguous() or triples.shape != (T, 3):
+        raise ValueError("triples must be a contiguous int64 (T, 3) tensor")
+    if (h_rows is None) != (t_rows is None):
+        raise ValueError("h_rows and t_rows must both be given or both None")
+    if h_rows is not None:
+        h_rows, t_rows = _f32c(h_rows), _f32c(t_rows)
+        if h_rows.shape != (T, d) or t_rows.shape != (T, d):
+            raise ValueError(f"h_rows / t_rows must be ({T}, {d})")
+    for name in ("gt", "ge", "true_score"):
+        t_ = out[name]
+        if t_.shape != (2, T) or not t_.is_contiguous():
+            raise ValueError(f"out[{name!r}] must be a contiguous (2, {T}) tensor")
+    ks, karr = _kvalues(k_values if k_values is not None else ())
+    if metrics is not None and (metrics["recip"].numel() != 2 * T or metrics["hits"].numel() != 2 * T * len(ks)):
+        raise ValueError("metrics tensors do not match (2T, nk)")
+    with _guard(dev):
+        _, stream = _enter(dev)
+        if T == 0:
+            return 0
+        ws = step_workspace(dev, stream.value, 2 * T)
+        check(lib().blp_rank_step(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rel_weight), rel_weight.shape[0],
+                                  _ptr(triples), T, _ptr(h_rows), _ptr(t_rows), T, int(group_triples),
+                                  _ptr(out["gt"]), _ptr(out["ge"]), _ptr(out["true_score"]), karr, len(ks),
+                                  _ptr(metrics["recip"]) if metrics else None, _ptr(metrics["hits"]) if metrics else None,
+                                  _ptr(metrics["sums"]) if metrics else None, _ptr(ws), stream), "blp_rank_step")
+    return _lib.last_launch_count()
+
+
+def rank_queries(model, ent, hq, tq, k_values=None, ent_offset=0, want_metrics=True):
+    """blp_rank_queries: rank unrelated head- / tail-prediction queries against the table without a score matrix.
+
+    hq = (tails (n, D), rels (n, D), true (n,) int64) or None: candidate e scored as score_fn(e, tails[i], rels[i]);
+    tq = (heads, rels, true) or None: score_fn(heads[i], e, rels[i]).  Returns dict(gt, ge, true_score[, recip, hits, sums])
+    over the n_hq + n_tq queries, head queries first (the reference's torch.cat order, train.py:149)."""
+    mid = model_id(model)
+    flat = [x for part in (hq, tq) if part is not None for x in part]
+    dev = _require_cuda(ent, *flat)
+    if ent.dtype != torch.float32 or not ent.is_contiguous() or ent.dim() != 2:
+        raise ValueError("ent must be a contiguous fp32 (N, D) tensor")
+    n, d = ent.shape
+
+    def prep(part):
+        if part is None:
+            return None, None, None, 0
+        a, r, true = part
+        a, r = _f32c(a).reshape(-1, d), _f32c(r).reshape(-1, d)
+        true = true.reshape(-1).to(torch.int64).contiguous()
+        if a.shape[0] != true.numel() or r.shape[0] != true.numel():
+            raise ValueError("query rows and true indices must have the same length")
+        return a, r, true, true.numel()
+
+    ha, hr, ht, n_hq = prep(hq)
+    ta, tr_, tt, n_tq = prep(tq)
+    nq = n_hq + n_tq
+    ks, karr = _kvalues(k_values if k_values is not None else ())
+    buf = torch.empty((3, nq), dtype=torch.int32, device=dev)
+    res = {"gt": buf[0], "ge": buf[1], "true_score": buf[2].view(torch.float32)}
+    m = alloc_metrics(dev, nq, len(ks)) if want_metrics else None
+    with _guard(dev):
+        _, stream = _enter(dev)
+        if nq > 0:
+            ws = step_workspace(dev, stream.value, nq)
+            check(lib().blp_rank_queries(mid, _ptr(ent), n, int(ent_offset), d, _ptr(ha), _ptr(hr), _ptr(ht), n_hq,
+                                         _ptr(ta), _ptr(tr_), _ptr(tt), n_tq, _ptr(res["gt"]), _ptr(res["ge"]),
+                                         _ptr(res["true_score"]), karr, len(ks), _ptr(m["recip"]) if m else None,
+                                         _ptr(m["hits"]) if m else None, _ptr(m["sums"]) if m else None, _ptr(ws), stream),
+                  "blp_rank_queries")
+    if m:
+        res.update(recip=m["recip"], hits=m["hits"].view(torch.bool), sums=m["sums"])
+    res["launches"] = _lib.last_launch_count() if nq > 0 else 0
+    return res
+
+
 def rank_metrics(gt, ge, k_values, per_query=True):
     """utils.py:106-109 + train.py:154-157 in one launch -> (recip (Q,1) f32, hits (Q,k) bool, sums f64 [1+k])."""
     dev = _require_cuda(gt, ge)

@@ -105,7 +105,7 @@ class DeviceFilterIndex:
     filtered ranks with one sparse correction launch per chunk and no host work."""
 
     def __init__(self, edges, ent2idx, num_rows, num_relations, device):
-        """edges: (E, 3) (head id, tail id, rel) -- e.g. list(graph.edges(keys=True)); ent2idx: id -> row or -1
+        """edges: (E, 3) (head id, tail id, rel) -- e.g. graph_edges(filtering_graph); ent2idx: id -> row or -1
         (None when ids are table rows); num_rows: rows of the whole entity table."""
         dev = torch.device(device)
         edges = torch.as_tensor(np.asarray(edges.cpu() if torch.is_tensor(edges) else edges, dtype=np.int64).reshape(-1, 3))
@@ -116,6 +116,15 @@ class DeviceFilterIndex:
             e2i = torch.as_tensor(np.asarray(ent2idx.cpu() if torch.is_tensor(ent2idx) else ent2idx, dtype=np.int64)).to(dev)
         self.workspace = ops.filter_index_build(edges.to(dev), e2i, self.num_rows, self.num_relations)
         self.device = dev
+
+
+def graph_edges(graph):
+    """(E, 3) int64 array of (head id, tail id, relation id) from the reference's filtering graph.
+
+    train.py:298-302 builds it with `nx.MultiDiGraph().add_weighted_edges_from(triples)`, which stores the relation id
+    in the edge attribute 'weight' (utils.get_triple_filters reads it back with `data='weight'`, utils.py:69,76).
+    `edges(keys=True)` would yield the multigraph key (0 for the first parallel edge, 1 for the second, ...) instead."""
+    return np.asarray(list(graph.edges(data='weight')), dtype=np.int64).reshape(-1, 3)
 
 
 def get_negative_sampling_indices(batch_size, num_negatives, repeats=1, *, device, seed=0, offset=0):

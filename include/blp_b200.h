@@ -136,6 +136,48 @@ int blp_rank_sweep_counts(int model, const float *ent, int64_t n_local, int64_t 
                           const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
                           int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, const float *true_score, void *stream);
 
+/* ---- the fused step: ONE launch per eval batch (train.py:141-157 for one batch of the reference's loop) ----
+ * As blp_rank_sweep without filter lists, plus the metrics: the true scores are computed per query group inside
+ * the sweep kernel, the counters accumulate in `workspace`, and the last CTA to finish writes gt / ge and --
+ * when sums != NULL -- utils.get_metrics' reciprocal ranks / hits (utils.py:106-109; recip [tail_off + t],
+ * hits [(tail_off + t) * nk], either may be NULL) and the train.py:154-157 accumulators sums[1 + nk] (fp64:
+ * sum of reciprocal ranks, hit counts).  d == 128 on a non-empty shard; other shapes run the separate kernels.
+ *   group_triples  triples per table pass: 0 = chosen from t; 2 / 4 / 8 / 16 / 32 forces it.  The reference's
+ *                  eval_batch_size is exactly this quantity (each batch streams the whole table once), so a
+ *                  Wikidata5M-style sweep at eval batch 2 is ONE call with t = all test triples, group_triples = 2.
+ *   workspace      blp_rank_step_workspace_bytes(tail_off + t) bytes, ZERO on first use; the kernel leaves it
+ *                  zeroed.  One per stream.  NULL (or tail_off + t > 16384): memset + separate metrics launch.
+ *   multi-GPU      pass sums = NULL, all-reduce gt / ge over the shards, then blp_rank_metrics. */
+int64_t blp_rank_step_workspace_bytes(int64_t out_len);
+int blp_rank_step(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                  const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                  const float *h_rows, const float *t_rows, int64_t tail_off, int group_triples,
+                  int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                  float *recip, uint8_t *hits, double *sums, void *workspace, void *stream);
+/* blp_rank_step with everything but the batch bound once: `plan` is a host object owned by the caller
+ * (blp_plan_destroy frees it); blp_plan_run(plan, triples, h_rows, t_rows, stream) is one step.  The reference
+ * calls the step every eval_batch_size = 64 triples (train.py:128), where argument marshalling is a visible
+ * share of a ~20 us step. */
+int blp_plan_create(void **plan_out, int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                    const float *rel_weight, int64_t num_rel, int64_t t, int64_t tail_off, int group_triples,
+                    int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                    float *recip, uint8_t *hits, double *sums, void *workspace);
+int blp_plan_run(void *plan, const int64_t *triples, const float *h_rows, const float *t_rows, void *stream);
+void blp_plan_destroy(void *plan);
+
+/* ---- get_metrics(score_fn(...), true_idx, k) without the score matrix (train.py:146-153 left untouched) ----
+ * Ranks unrelated queries against the table: n_hq head-prediction queries -- candidate row e scored as
+ * score_fn(e, hq_tails[i], hq_rels[i]) (train.py:146), true candidate row hq_true[i] (global id) -- followed by
+ * n_tq tail-prediction queries score_fn(tq_heads[i], e, tq_rels[i]) (train.py:147) with true candidate tq_true[i].
+ * Query rows are dense [n, d]; outputs (gt, ge, true_score, recip, hits) hold the head queries first, i.e. the
+ * row order of torch.cat((heads_predictions, tails_predictions)) (train.py:149).  One launch when n_hq == n_tq,
+ * d == 128 and a workspace (blp_rank_step_workspace_bytes(n_hq + n_tq)) is given. */
+int blp_rank_queries(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                     const float *hq_tails, const float *hq_rels, const int64_t *hq_true, int64_t n_hq,
+                     const float *tq_heads, const float *tq_rels, const int64_t *tq_true, int64_t n_tq,
+                     int32_t *gt, int32_t *ge, float *true_score, const int64_t *k_values_host, int nk,
+                     float *recip, uint8_t *hits, double *sums, void *workspace, void *stream);
+
 /* ---- tensor-core ("fast") mode of the sweep: distmult / complex / simple, d = 128 ----
  * The bilinear scores are linear in the candidate row once the query side is folded
  * (models.py:226-248 with the candidate factored out), so the sweep is a (2t x 128) x (128 x n)
@@ -295,6 +337,11 @@ int blp_profile_events(int which, void *start_event, void *stop_event);
 /* Number of kernels the last call on this thread launched (bench.py's
  * `gpu_launches` is counted from this). */
 int blp_last_launch_count(void);
+
+/* measurement aid: sweep launches of this host thread write 16 globaltimer (ns) slots per CTA into `buffer`
+ * (>= 148 * 16 uint64; slots: 0 start, 1 setup done, 2 true scores, 3 operands folded, 4 first tile landed,
+ * 5 tiles done, 6 ticket taken, 7 epilogue done, 8 #segments, 9 #work items); NULL switches it off. */
+int blp_debug_timestamps(void *buffer);
 
 #ifdef __cplusplus
 }

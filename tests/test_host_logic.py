@@ -210,3 +210,40 @@ def test_torch_port_row_restatements_are_consistent():
     assert bool(((repl // 2) != torch.arange(8).view(8, 1)).all())          # the other comes from another row
     x = torch.randn(5, 128)
     assert np.array_equal(torch_port.normalize_rows(x).numpy(), np_oracle.l2_normalize_rows(x.numpy()))
+
+
+def test_filter_index_from_networkx_graph_as_integration_md():
+    """INTEGRATION.md Level 1 builds the index from the reference's nx.MultiDiGraph (train.py:298-302:
+    add_weighted_edges_from stores the relation as the edge WEIGHT); the result must equal utils.get_triple_filters
+    restated literally over that graph (utils.py:46-83), including parallel edges with different relations."""
+    nx = pytest.importorskip("networkx")
+    rng = np.random.default_rng(5)
+    n_ids, n_rel, n_edges = 40, 4, 400
+    all_triples = np.stack([rng.integers(0, n_ids, n_edges), rng.integers(0, n_ids, n_edges),
+                            rng.integers(0, n_rel, n_edges)], axis=1)
+    all_triples[1] = all_triples[0]; all_triples[1, 2] = (all_triples[0, 2] + 1) % n_rel    # parallel edge, other relation
+    all_triples[2] = all_triples[0]                                                          # exact duplicate edge
+    graph = nx.MultiDiGraph()
+    graph.add_weighted_edges_from(all_triples.tolist())                                      # train.py:302
+    entities = torch.from_numpy(rng.permutation(n_ids)[:30].astype(np.int64))                # 10 ids have no table row
+    ent2idx = make_ent2idx(entities, n_ids - 1)
+    edges = blp_b200.graph_edges(graph)
+    assert sorted(map(tuple, edges.tolist())) == sorted(map(tuple, all_triples.tolist()))
+    # edges(keys=True) would NOT carry the relation (the ADVICE r1 bug): keys are 0, 1, ... per parallel edge
+    assert sorted(k for _, _, k in graph.edges(keys=True)) != sorted(all_triples[:, 2].tolist())
+    fidx = TripleFilterIndex(edges, ent2idx)
+    test = all_triples[rng.permutation(n_edges)[:64]]
+    test = test[(ent2idx[test[:, 0]] >= 0).numpy() & (ent2idx[test[:, 1]] >= 0).numpy()]
+    hf, tf = fidx.dense_masks(test, len(entities))
+    # utils.get_triple_filters, literally, over the nx graph
+    rhf = np.zeros((len(test), len(entities)), bool)
+    rtf = np.zeros_like(rhf)
+    for i, (head, tail, rel) in enumerate(test.tolist()):
+        for (h, t, r) in graph.out_edges(head, data='weight'):
+            if r == rel and t != tail and ent2idx[t] != -1:
+                rtf[i, ent2idx[t]] = True
+        for (h, t, r) in graph.in_edges(tail, data='weight'):
+            if r == rel and h != head and ent2idx[h] != -1:
+                rhf[i, ent2idx[h]] = True
+    assert np.array_equal(hf, rhf) and np.array_equal(tf, rtf)
+    assert rhf.sum() + rtf.sum() > 0

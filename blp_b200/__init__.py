@@ -12,7 +12,7 @@ Public surface (same names as the reference's models.py / utils.py):
 
 All computation runs in libblp_b200.so (blp_b200/csrc, C ABI in include/blp_b200.h).
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, lazy, ops  # noqa: F401
 from .ops import store_rows  # noqa: F401
 from ._lib import BlpError  # noqa: F401
 from .graphs import GraphedLossStep  # noqa: F401
@@ -26,13 +26,19 @@ from .utils import (DeviceFilterIndex, TripleFilterIndex, get_metrics, get_negat
 __version__ = "0.1.0"
 
 
-def patch(models_module, utils_module=None):
+def patch(models_module, utils_module=None, lazy_scores=True):
     """Rebind the hot path inside the reference's own modules.
 
     After `import models, utils; blp_b200.patch(models, utils)` every reference model class
     (BertEmbeddingsLP, BOW, DKRL, ...) built afterwards binds the CUDA score / loss functions
     (models.py:16-24, 31-34), `compute_loss` is the fused kernel, and train.py's
     `utils.get_metrics(...)` calls run on the GPU.  train.py itself is untouched.
+
+    lazy_scores (default on): `score_fn` on the eval broadcast of train.py:146-147 returns a score-matrix HANDLE
+    (blp_b200.lazy.LazyScores) that torch.cat, utils.get_metrics and the filter statement train.py:165 consume without
+    materialising the (2B, N) matrix -- the unmodified eval loop then runs the fused sweep kernel, one launch per
+    batch -- and utils.get_triple_filters returns filter handles backed by a device-resident index built once per
+    filtering graph.  Any other use of a handle materialises it with the exact kernels.
     """
     from . import models as _m
     for name in ("transe_score", "distmult_score", "complex_score", "simple_score",
@@ -41,4 +47,7 @@ def patch(models_module, utils_module=None):
     models_module.LinkPrediction.compute_loss = _m.compute_loss
     if utils_module is not None:
         utils_module.get_metrics = get_metrics
+        orig = getattr(utils_module.get_triple_filters, "__wrapped__", utils_module.get_triple_filters)
+        utils_module.get_triple_filters = lazy.make_get_triple_filters(orig) if lazy_scores else orig
+    lazy.enable(lazy_scores)
     return models_module

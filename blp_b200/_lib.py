@@ -56,6 +56,10 @@ SYMBOLS = {
     "blp_filter_index_build": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "blp_filter_correct": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64,
                                   _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_filter_correct_rows": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
+    "blp_filter_correct_mask": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64,
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "blp_mrr_breakdown": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "blp_negative_sample": (_i32, [_i64, _i64, _i64, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "blp_store_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _i64, _vp]),

@@ -127,6 +127,53 @@ __global__ void filter_correct_indexed_kernel(int model, const float *__restrict
     }
 }
 
+// The same correction from the reference's own dense mask (train.py:160-165: `pred[filter_mask] = pred.min() - 1.0`):
+// one warp per query scans its mask row and re-scores only the masked candidates.  Queries are independent
+// (head-prediction queries [0, n_hq), then tail-prediction queries).  A masked TRUE candidate (never produced by
+// utils.get_triple_filters, utils.py:71,78) gets the reference's semantics too: its score becomes min - 1, so every
+// unmasked candidate ranks above it and every candidate ties or beats it.
+__global__ void filter_correct_mask_kernel(int model, const float *__restrict__ ent, long long n_local, int d,
+                                           const RowRef hq_h, const RowRef hq_t, const RowRef hq_r, long long n_hq,
+                                           const RowRef tq_h, const RowRef tq_t, const RowRef tq_r, long long n_tq,
+                                           const long long *__restrict__ hq_true, const long long *__restrict__ tq_true,
+                                           long long ent_offset, const unsigned char *__restrict__ mask, long long ld_mask,
+                                           const float *__restrict__ true_score, const int *__restrict__ gt,
+                                           const int *__restrict__ ge, int *__restrict__ gt_f, int *__restrict__ ge_f) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= n_hq + n_tq) return;
+    const bool head_pred = q < n_hq;
+    const long long i = head_pred ? q : q - n_hq;
+    const float st = true_score[q];
+    const float *h = (head_pred ? hq_h : tq_h).row(i, d), *t = (head_pred ? hq_t : tq_t).row(i, d),
+                *r = (head_pred ? hq_r : tq_r).row(i, d);
+    const long long truth = (head_pred ? hq_true[i] : tq_true[i]) - ent_offset;
+    const unsigned char *row = mask + q * ld_mask;
+    int cg = 0, ce = 0, nm = 0;
+    for (long long c = lane; c < n_local; c += 32) {
+        if (!row[c]) continue;
+        ++nm;
+        if (c == truth) continue;
+        const float *e = ent + c * d;
+        const float s = head_pred ? score_exact_dyn(model, e, t, r, d) : score_exact_dyn(model, h, e, r, d);
+        cg += s > st;
+        ce += s >= st;
+    }
+    cg = __reduce_add_sync(0xffffffffu, cg);
+    ce = __reduce_add_sync(0xffffffffu, ce);
+    nm = __reduce_add_sync(0xffffffffu, nm);
+    if (lane == 0) {
+        const bool truth_masked = truth >= 0 && truth < n_local && row[truth];
+        if (truth_masked) {
+            gt_f[q] = (int)(n_local - nm);
+            ge_f[q] = (int)n_local;
+        } else {
+            gt_f[q] = gt[q] - cg;
+            ge_f[q] = ge[q] - ce;
+        }
+    }
+}
+
 // train.py:173-188: out[0..3) mrr_by_position (both new, head new, tail new), out[3..6) counts,
 // out[6..14) mrr_by_category [2][4] (head prediction row, tail prediction row), out[14..18) category counts.
 __global__ void __launch_bounds__(1024) mrr_breakdown_kernel(const float *__restrict__ recip, long long t, long long tail_off,
@@ -253,6 +300,70 @@ extern "C" int blp_filter_correct(int model, const float *ent, int64_t n_local, 
         model, ent, n_local, ent_offset, d, h, tt, r, tr, t, tail_off,
         reinterpret_cast<const unsigned long long *>(ws + L.off_tails),
         reinterpret_cast<const unsigned long long *>(ws + L.off_heads), L.e_pad, n_rows, num_rel, true_score, gt, ge, gt_f, ge_f);
+    count_launch();
+    BLP_CUDA(cudaGetLastError());
+    return BLP_OK;
+}
+
+// blp_filter_correct for the score-matrix path (train.py:141-171 untouched): the lookup keys come from
+// `triples` (head row, tail row, relation id), the operand rows are the dense (t, d) blocks the call site gathered
+// (head_embs, tail_embs, rel_embs of train.py:141-143).
+extern "C" int blp_filter_correct_rows(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                       const int64_t *triples, int64_t t, const float *h_rows, const float *t_rows,
+                                       const float *r_rows, const void *index_ws, int64_t num_edges, int64_t n_rows,
+                                       int64_t num_rel, int64_t tail_off, const float *true_score, const int32_t *gt,
+                                       const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream) {
+    reset_launch_count();
+    if (model < 0 || model > 3) { set_error("unknown relational model id %d", model); return BLP_EINVAL; }
+    if (d <= 0 || ((model == BLP_MODEL_COMPLEX || model == BLP_MODEL_SIMPLE) && (d & 1))) { set_error("bad d %d", d); return BLP_EDIM; }
+    if (t < 0 || n_local < 0 || num_edges < 0 || n_rows <= 0 || num_rel <= 0 || tail_off < t) { set_error("bad size argument"); return BLP_EINVAL; }
+    if (t == 0) return BLP_OK;
+    if (!triples || !h_rows || !t_rows || !r_rows || !index_ws || !true_score || !gt || !ge || !gt_f || !ge_f || (n_local > 0 && !ent)) {
+        set_error("null pointer argument");
+        return BLP_EINVAL;
+    }
+    FilterLayout L;
+    int rc = filter_layout(num_edges, &L);
+    if (rc) return rc;
+    const unsigned char *ws = reinterpret_cast<const unsigned char *>(index_ws);
+    const int threads = 128;
+    const long long blocks = (2 * t * 32 + threads - 1) / threads;
+    filter_correct_indexed_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        model, ent, n_local, ent_offset, d, dense_rows(h_rows), dense_rows(t_rows), dense_rows(r_rows), (const long long *)triples, t,
+        tail_off, reinterpret_cast<const unsigned long long *>(ws + L.off_tails),
+        reinterpret_cast<const unsigned long long *>(ws + L.off_heads), L.e_pad, n_rows, num_rel, true_score, gt, ge, gt_f, ge_f);
+    count_launch();
+    BLP_CUDA(cudaGetLastError());
+    return BLP_OK;
+}
+
+// train.py:164-167 from the reference's own dense bool mask: filtered counters of the n_hq + n_tq queries of
+// blp_rank_queries (same query arguments, same output order).  mask is (n_hq + n_tq, ld_mask) bytes, column j =
+// candidate row ent_offset + j.
+extern "C" int blp_filter_correct_mask(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                       const float *hq_tails, const float *hq_rels, const int64_t *hq_true, int64_t n_hq,
+                                       const float *tq_heads, const float *tq_rels, const int64_t *tq_true, int64_t n_tq,
+                                       const uint8_t *mask, int64_t ld_mask, const float *true_score, const int32_t *gt,
+                                       const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream) {
+    reset_launch_count();
+    if (model < 0 || model > 3) { set_error("unknown relational model id %d", model); return BLP_EINVAL; }
+    if (d <= 0 || ((model == BLP_MODEL_COMPLEX || model == BLP_MODEL_SIMPLE) && (d & 1))) { set_error("bad d %d", d); return BLP_EDIM; }
+    if (n_hq < 0 || n_tq < 0 || n_local <= 0 || ld_mask < n_local) { set_error("bad size argument"); return BLP_EINVAL; }
+    const int64_t nq = n_hq + n_tq;
+    if (nq == 0) return BLP_OK;
+    if (!ent || !mask || !true_score || !gt || !ge || !gt_f || !ge_f || (n_hq > 0 && (!hq_tails || !hq_rels || !hq_true)) ||
+        (n_tq > 0 && (!tq_heads || !tq_rels || !tq_true))) {
+        set_error("null pointer argument");
+        return BLP_EINVAL;
+    }
+    const RowRef hq_h = RowRef{ent, (const long long *)hq_true, 1, ent_offset, n_local};
+    const RowRef tq_t = RowRef{ent, (const long long *)tq_true, 1, ent_offset, n_local};
+    const int threads = 128;
+    const long long blocks = (nq * 32 + threads - 1) / threads;
+    filter_correct_mask_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        model, ent, n_local, d, hq_h, dense_rows(hq_tails), dense_rows(hq_rels), n_hq, dense_rows(tq_heads), tq_t,
+        dense_rows(tq_rels), n_tq, (const long long *)hq_true, (const long long *)tq_true, ent_offset, mask, ld_mask, true_score,
+        gt, ge, gt_f, ge_f);
     count_launch();
     BLP_CUDA(cudaGetLastError());
     return BLP_OK;

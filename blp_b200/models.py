@@ -14,28 +14,37 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import lazy, ops
 
 
 # ---------------------------------------------------------------- score_fn ----
+def _score(model, heads, tails, rels):
+    """score_fn(heads, tails, rels).  For the eval broadcast of train.py:146-147 -- (1,N,D) against (B,1,D) rows, no
+    grad -- with lazy score matrices switched on (blp_b200.patch), the result is a `lazy.LazyScores` handle that
+    torch.cat / utils.get_metrics / `pred[mask] = pred.min() - 1` consume without the (B, N) matrix ever existing;
+    any other use materialises it with the same exact kernels."""
+    handle = lazy.maybe_lazy_score(model, heads, tails, rels)
+    return handle if handle is not None else ops.score(model, heads, tails, rels)
+
+
 def transe_score(heads, tails, rels):
     """models.py:222-223  -||h + r - t||_1 over the last dim."""
-    return ops.score("transe", heads, tails, rels)
+    return _score("transe", heads, tails, rels)
 
 
 def distmult_score(heads, tails, rels):
     """models.py:226-227  sum(h * r * t)."""
-    return ops.score("distmult", heads, tails, rels)
+    return _score("distmult", heads, tails, rels)
 
 
 def complex_score(heads, tails, rels):
     """models.py:230-239  Re(<r, h, conj(t)>) on (re | im) halves."""
-    return ops.score("complex", heads, tails, rels)
+    return _score("complex", heads, tails, rels)
 
 
 def simple_score(heads, tails, rels):
     """models.py:242-248  SimplE on (head-role | tail-role) halves, / 2."""
-    return ops.score("simple", heads, tails, rels)
+    return _score("simple", heads, tails, rels)
 
 
 SCORE_FNS = {"transe": transe_score, "distmult": distmult_score, "complex": complex_score, "simple": simple_score}

@@ -499,6 +499,59 @@ def filter_correct(model, ent, rel_weight, triples, out, lo, hi, index_ws, num_e
     return _lib.last_launch_count()
 
 
+def filter_correct_rows(model, ent, rows, h_rows, t_rows, r_rows, index, raw, gt_f, ge_f, ent_offset=0):
+    """blp_filter_correct_rows: filtered counters of the 2T queries of a (head predictions | tail predictions) score
+    handle from the device filter index; rows (T, 3) = (head row, tail row, relation id) are the lookup keys, the
+    dense (T, D) operand rows are the call site's own gathers (train.py:141-143)."""
+    mid = model_id(model)
+    dev = _require_cuda(ent, rows, h_rows, t_rows, r_rows, gt_f, ge_f)
+    n, d = ent.shape
+    T = rows.shape[0]
+    if rows.dtype != torch.int64 or not rows.is_contiguous() or rows.shape != (T, 3):
+        raise ValueError("rows must be a contiguous int64 (T, 3) tensor")
+    h_rows, t_rows, r_rows = (_f32c(x) for x in (h_rows, t_rows, r_rows))
+    with _guard(dev):
+        _, stream = _enter(dev)
+        if T > 0:
+            check(lib().blp_filter_correct_rows(mid, _ptr(ent), n, int(ent_offset), d, _ptr(rows), T, _ptr(h_rows), _ptr(t_rows),
+                                                _ptr(r_rows), _ptr(index.workspace), index.num_edges, index.num_rows,
+                                                index.num_relations, T, _ptr(raw["true_score"]), _ptr(raw["gt"]),
+                                                _ptr(raw["ge"]), _ptr(gt_f), _ptr(ge_f), stream), "blp_filter_correct_rows")
+    return gt_f, ge_f
+
+
+def filter_correct_mask(model, ent, hq, tq, mask, raw, gt_f, ge_f, ent_offset=0):
+    """blp_filter_correct_mask: filtered counters from the reference's dense (Q, N) bool mask (train.py:160-167) for the
+    queries of `rank_queries(model, ent, hq, tq)`; raw = its gt / ge / true_score."""
+    mid = model_id(model)
+    flat = [x for part in (hq, tq) if part is not None for x in part]
+    dev = _require_cuda(ent, mask, gt_f, ge_f, *flat)
+    n, d = ent.shape
+
+    def prep(part):
+        if part is None:
+            return None, None, None, 0
+        a, r, true = part
+        true = true.reshape(-1).to(torch.int64).contiguous()
+        return _f32c(a).reshape(-1, d), _f32c(r).reshape(-1, d), true, true.numel()
+
+    ha, hr, ht, n_hq = prep(hq)
+    ta, tr_, tt, n_tq = prep(tq)
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    if mask.dim() != 2 or mask.shape[0] != n_hq + n_tq or mask.shape[1] < n or mask.stride(1) != 1:
+        raise ValueError("mask must be a (Q, N) bool tensor with unit column stride")
+    with _guard(dev):
+        _, stream = _enter(dev)
+        if n_hq + n_tq > 0:
+            check(lib().blp_filter_correct_mask(mid, _ptr(ent), n, int(ent_offset), d, _ptr(ha), _ptr(hr), _ptr(ht), n_hq,
+                                                _ptr(ta), _ptr(tr_), _ptr(tt), n_tq, _ptr(mask),
+                                                mask.stride(0) if mask.shape[0] > 1 else mask.shape[1],
+                                                _ptr(raw["true_score"]), _ptr(raw["gt"]), _ptr(raw["ge"]), _ptr(gt_f),
+                                                _ptr(ge_f), stream), "blp_filter_correct_mask")
+    return gt_f, ge_f
+
+
 def mrr_breakdown(recip, triples_ids, is_new=None, rel_categories=None):
     """train.py:173-188 (utils.split_by_new_position / split_by_category) -> float64 device tensor [18]:
     mrr_by_position[3], position counts[3], mrr_by_category[2*4], category counts[4]."""

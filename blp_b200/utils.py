@@ -7,11 +7,15 @@ rebuilds a dense (B, N) bool mask per batch with Python loops over graph edges).
 import numpy as np
 import torch
 
-from . import ops
+from . import lazy, ops
 
 
 def get_metrics(pred_scores, true_idx, k_values):
     """utils.py:86-111: (reciprocals (Q,1) f32, hits (Q,k) bool) from a (Q,N) score matrix."""
+    if isinstance(pred_scores, lazy.LazyScores):
+        if pred_scores._dense is None:
+            return pred_scores.metrics(true_idx, k_values)     # fused: the score matrix never exists
+        pred_scores = pred_scores._dense
     gt, ge = ops.rank_counts(pred_scores, true_idx)
     return ops.metrics_from_counts(gt, ge, k_values)
 

@@ -281,6 +281,24 @@ int blp_filter_correct(int model, const float *ent, int64_t n_local, int64_t ent
                        int64_t n_rows, int64_t tail_off, const float *true_score, const int32_t *gt,
                        const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream);
 
+/* blp_filter_correct for the score-matrix path (train.py:141-171 left untouched): the lookup keys come from
+ * `triples` (t, 3) = (head row, tail row, relation id); the operand rows are the dense (t, d) blocks the call site
+ * gathered itself (head_embs, tail_embs, rel_embs of train.py:141-143). */
+int blp_filter_correct_rows(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                            const int64_t *triples, int64_t t, const float *h_rows, const float *t_rows,
+                            const float *r_rows, const void *index_ws, int64_t num_edges, int64_t n_rows,
+                            int64_t num_rel, int64_t tail_off, const float *true_score, const int32_t *gt,
+                            const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream);
+/* train.py:164-167 from the reference's own dense bool mask (`pred[filter_mask] = pred.min() - 1.0` followed by
+ * get_metrics): filtered counters of the n_hq + n_tq queries of blp_rank_queries (same query arguments and output
+ * order).  mask: (n_hq + n_tq, ld_mask) bytes, column j = candidate row ent_offset + j; only the masked candidates
+ * are re-scored.  A masked true candidate gets the reference's semantics (its score becomes min - 1). */
+int blp_filter_correct_mask(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                            const float *hq_tails, const float *hq_rels, const int64_t *hq_true, int64_t n_hq,
+                            const float *tq_heads, const float *tq_rels, const int64_t *tq_true, int64_t n_tq,
+                            const uint8_t *mask, int64_t ld_mask, const float *true_score, const int32_t *gt,
+                            const int32_t *ge, int32_t *gt_f, int32_t *ge_f, void *stream);
+
 /* ---- next row f2  MRR breakdowns of train.py:173-188 (utils.py:114-168) in one launch ---------
  *   recip      reciprocal ranks, head query i at [i], tail query i at [tail_off + i]
  *   triples    [t, 3] int64 (head id, tail id, rel) ENTITY IDS (as the reference's loops see them)

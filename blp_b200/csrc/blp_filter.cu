@@ -122,8 +122,17 @@ __global__ void filter_correct_indexed_kernel(int model, const float *__restrict
     cg = __reduce_add_sync(0xffffffffu, cg);
     ce = __reduce_add_sync(0xffffffffu, ce);
     if (lane == 0) {
-        gt_f[o] = gt[o] - cg;
-        ge_f[o] = ge[o] - ce;
+        // Exact mode: the raw counters and this correction use the same arithmetic, so 0 <= gt_f < ge_f always holds
+        // where the true entity lives.  Tensor-core mode counts with split-FP16 scores but corrects with exact ones: a
+        // filtered candidate inside the tolerance band around s_true can be judged differently by the two, so the
+        // filtered counters are clamped to their valid range (gt_f >= 0; ge_f >= gt_f, and > gt_f on the shard that
+        // holds the true entity, which always ties itself).
+        const long long trow = truth - ent_offset;
+        const int g = max(gt[o] - cg, 0);
+        int e = max(ge[o] - ce, g);
+        if (trow >= 0 && trow < n_local && st == st) e = max(e, g + 1);
+        gt_f[o] = g;
+        ge_f[o] = e;
     }
 }
 

@@ -101,3 +101,35 @@ def test_fast_mode_rejects_transe_and_other_widths(cuda_device):
     ent64 = torch.randn(300, 64)
     with pytest.raises(ValueError):
         ops.fast_table(ent64.to(dev))
+
+
+@pytest.mark.parametrize("model", FAST_MODELS)
+def test_fast_filtered_counters_stay_valid_with_tied_filtered_candidates(model, cuda_device):
+    """the raw counters of the tensor-core mode come from split-FP16 scores, the filter correction re-scores
+    with exact fp32.  Filtered candidates that TIE with the true score (known-true triples score near s_true; here exact
+    duplicates of the true entity's row) may be judged differently by the two: the filtered counters must still be
+    valid ranks (gt_f >= 0, ge_f >= gt_f + 1), never a zero / negative average rank."""
+    n, b, n_rel = 400, 24, 5
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=77, n_rel=n_rel)
+    edges = []
+    for i in range(b):
+        dup_h, dup_t = 300 + i, 330 + i                    # duplicates of the true head / tail rows, both filtered
+        ent[dup_h] = ent[heads[i]]
+        ent[dup_t] = ent[tails[i]]
+        edges += [(dup_h, int(tails[i]), int(rels[i])), (int(heads[i]), dup_t, int(rels[i]))]
+    # make the true triples the best-scoring ones so that gt is tiny and a miscounted tie would go negative
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    fidx = blp_b200.DeviceFilterIndex(np.array(edges, np.int64), None, n, n_rel, dev)
+    exact = blp_b200.rank_sweep(model, e, r, triples, filter_index=fidx)
+    fast = blp_b200.rank_sweep(model, e, r, triples, filter_index=fidx, mode="fast")
+    for out in (exact, fast):
+        gt_f, ge_f = out["gt_f"].cpu(), out["ge_f"].cpu()
+        assert bool((gt_f >= 0).all()) and bool((ge_f >= gt_f + 1).all())
+        assert bool(torch.isfinite(out["recip_f"]).all()) and float(out["recip_f"].max()) <= 1.0
+    # exact mode: the duplicate is removed from the ties exactly
+    assert torch.equal(exact["ge_f"], exact["ge"] - 1) and torch.equal(exact["gt_f"], exact["gt"])
+    # fast mode: at most the tolerance-band candidates (here the one duplicate per query) may differ
+    assert int((fast["ge_f"].cpu() - exact["ge_f"].cpu()).abs().max()) <= 1
+    assert int((fast["gt_f"].cpu() - exact["gt_f"].cpu()).abs().max()) <= 1

@@ -1,11 +1,17 @@
 #!/bin/bash
-# N-GPU pass: NCCL sharded-sweep tests + bench under torchrun.  gpurun --gpus N --timeout 900 -- 'bash tools/gpu_multi.sh N'
+# N-GPU pass: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_multi.sh N'
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-echo "== pytest multi"; timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_multi.txt
-echo "== bench x$N"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --gpus $N --steps 50 --warmup 5 --no-cpu-baseline 2> gpurun_out/bench_x$N.err | tee gpurun_out/bench_x$N.json | cut -c1-200; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_x$N.err | tail -5
-echo "== bench reference arm x$N"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-  bench.py --impl reference --gpus $N --steps 2 --warmup 1 2> gpurun_out/bench_ref_x$N.err | tee gpurun_out/bench_ref_x$N.json | cut -c1-200
+echo "== NCCL tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -q --tb=short 2>&1 | tail -5 | tee gpurun_out/pytest_multi.txt
+echo "== bench x$N"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  bench.py --gpus $N --steps 20 --warmup 5 2> gpurun_out/bench_x$N.err > gpurun_out/bench_x$N.json
+tail -3 gpurun_out/bench_x$N.err
+python - "$N" <<'PY'
+import json, sys
+n = sys.argv[1]
+d = json.loads(open(f"gpurun_out/bench_x{n}.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "parity", d["sharded_parity"])
+print(json.dumps(d["wikidata5m_scale_sweep"], indent=1))
+PY

@@ -334,6 +334,12 @@ static int rank_impl(const RankJob &j, cudaStream_t st) {
             fill_sweep_args(a, j);
             const int rc = launch_sweep_dyn(model, a, st);
             if (rc) return rc;
+        } else if (sweep_wide_supports(model, d, j.ent) && job_rows_aligned(j) && j.roles == 3) {
+            // TransE at the BOW widths (d = 300 / 768, ...): TMA-tiled, the row streams through in 64-float stages
+            SweepArgs a{};
+            fill_sweep_args(a, j);
+            const int rc = launch_sweep_wide(a, d, st);
+            if (rc) return rc;
         } else {
             const int threads = 256;
             long long bx = (n_local + threads - 1) / threads;

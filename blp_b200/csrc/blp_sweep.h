@@ -216,6 +216,9 @@ struct SweepArgs {
 };
 
 int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st);
+// TransE at any row width d % 4 == 0 (blp_sweep_wide.cu): counting only, true_score given, counters zeroed
+bool sweep_wide_supports(int model, int d, const float *ent);
+int launch_sweep_wide(const SweepArgs &a, int d, cudaStream_t st);
 
 // tensor-core fast mode (blp_fast.cu)
 long long fast_table_ws_bytes(long long n_local);

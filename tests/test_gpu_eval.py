@@ -261,3 +261,27 @@ def test_native_sweep_sharded_with_pregathered_rows(model, cuda_device):
         acc_gt += part["gt"]
         acc_ge += part["ge"]
     assert torch.equal(acc_gt, full["gt"]) and torch.equal(acc_ge, full["ge"])
+
+
+@pytest.mark.parametrize("d", (4, 32, 36, 64, 300, 384, 388, 768, 772, 1536, 2048))
+@pytest.mark.parametrize("n,b", [(130, 1), (257, 3), (1000, 9), (3000, 40)])
+def test_wide_transe_sweep_vs_oracle(d, n, b, cuda_device):
+    """TransE at the BOW encoder widths (utils.py:11-19: 300 / 768) and every register-tile shape of the TMA-tiled
+    wide kernel (blp_sweep_wide.cu): rows stream through shared memory in 64-float stages, zero padded to 32 floats."""
+    ent, rel, heads, tails, rels = make_inputs("transe", n, d, b, seed=d + n)
+    ent[n - 1] = ent[3]                # exact ties
+    heads[0] = 3
+    co = c_oracle.eval_rank("transe", ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy())
+    e, r = ent.to(cuda_device), rel.to(cuda_device)
+    triples = torch.stack([heads, tails, rels], 1).to(cuda_device)
+    out = blp_b200.rank_sweep("transe", e, r, triples)
+    assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+    assert np.array_equal(out["gt"].reshape(-1).cpu().numpy(), co["gt"])
+    assert np.array_equal(out["ge"].reshape(-1).cpu().numpy(), co["ge"])
+    # two row shards add up (entity-sharded sweeps at BOW widths)
+    cut = n // 3
+    h_rows, t_rows = e[triples[:, 0]], e[triples[:, 1]]
+    a = blp_b200.rank_sweep("transe", e[:cut].contiguous(), r, triples, h_rows=h_rows, t_rows=t_rows)
+    c = blp_b200.rank_sweep("transe", e[cut:].contiguous(), r, triples, ent_offset=cut, h_rows=h_rows, t_rows=t_rows)
+    assert torch.equal(a["gt"] + c["gt"], out["gt"]) and torch.equal(a["ge"] + c["ge"], out["ge"])

@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libblp_b200.so")
+SO_PATH = os.environ.get("BLP_B200_LIB") or os.path.join(_HERE, "libblp_b200.so")    # BLP_B200_LIB: tuning builds
 
 MODELS = {"transe": 0, "distmult": 1, "complex": 2, "simple": 3}
 LOSSES = {"margin": 0, "nll": 1}

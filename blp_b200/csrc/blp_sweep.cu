@@ -37,6 +37,14 @@
 
 #include "blp_sweep.h"
 
+// unroll factors of the TransE position loop (tuning: instruction-cache footprint vs. scheduling freedom)
+#ifndef BLP_UNROLL_CC
+#define BLP_UNROLL_CC 8
+#endif
+#ifndef BLP_UNROLL_CC_SHARED
+#define BLP_UNROLL_CC_SHARED 4
+#endif
+
 namespace blp {
 
 constexpr int kPitch = 132;                   // smem row pitch (floats) of the padded (bilinear) tile layout
@@ -291,7 +299,7 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
         // strictly sequential L1 accumulation, natural order
         // the kernel holds two copies of this loop nest (shared / per-query relation); the shared one is unrolled
         // less so that the hot loop bodies stay inside the instruction cache (ncu: stall_no_instructions)
-        constexpr int kUnrollCC = SHARED_R ? 4 : 8;
+        constexpr int kUnrollCC = SHARED_R ? BLP_UNROLL_CC_SHARED : BLP_UNROLL_CC;
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb)
 #pragma unroll kUnrollCC
@@ -695,8 +703,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #pragma unroll
         for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
         // TransE, mixed role: do this slot's head-prediction triples share one relation row?  (warp-uniform)
+#ifndef BLP_SHARED_R
+#define BLP_SHARED_R 1
+#endif
         bool shared_r = false;
-        if (MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
+        if (BLP_SHARED_R && MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
             const long long tr0 = t0 + QM::triple(slot, 0);
             shared_r = tr0 + C::TQP <= args.b;
             if (shared_r) {
@@ -716,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
                 const TileView<MODEL> tv(&sm.ctile[buf][0], row_off);
-                if (QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4 && shared_r)
+                if (BLP_SHARED_R && QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4 && shared_r)
                     score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
                 else if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(tv, qv, args.negzero2, sp);

@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- triples scored / second on the BLP scoring-and-ranking hot path (BASELINE.json).
 
-One STEP = one pass of the hot path over one evaluation set of synthetic FB15k-237-shaped input, in C = T / E
-sub-steps (T = 20,480 test triples, E = 1,024 per sub-step); every sub-step is
-  * one training step of LinkPrediction.compute_loss forward + backward (models.py:51-70)
-    on B positives with K in-batch negatives each              -> B * (K + 1) triples scored
-  * E test triples ranked against ALL N entities, heads and tails (train.py:128-157), one fused launch
-                                                                -> 2 * E * N triples scored
+One STEP = one pass of the hot path over one evaluation set of synthetic FB15k-237-shaped input:
+  * C = T / 1024 = 20 training steps of LinkPrediction.compute_loss forward + backward (models.py:51-70)
+    on B positives with K in-batch negatives each              -> C * B * (K + 1) triples scored
+  * the T = 20,480 test triples ranked against ALL N entities, heads and tails (train.py:128-157): exact mode = ONE
+    fused launch for the whole sweep (true scores, sweep, counters), triples in relation-aligned order
+                                                                -> 2 * T * N triples scored
+(the reference arm samples 1 / C of it: one training step + 1,024 test triples in eval batches of 64)
 `value` = triples scored per second with inputs resident in HBM (CUDA-event timed, max over ranks);
 `e2e`   = the same metric through the public API with HOST (pinned) inputs, H2D/D2H inside the timed region.
 `roofline` = the dominant kernel (the eval sweep) against the bound that BINDS it (FP32 pipe for the exact-order FB sweep);
@@ -126,12 +127,13 @@ def step_triples(w, e):
 def config_dict(args, w, e, world):
     """Identical in both arms (the reference arm processes a bounded SAMPLE of this step, see cpu_baseline.sample)."""
     c = substeps(w, e)
-    return {"workload": f"synthetic {w['dataset']} ({w['n']} entities, {w['r']} relations) BLP-{w['model']} dim={w['d']}: one "
-                        f"pass over the {c * e} test triples in {c} sub-steps of [1 compute_loss fwd+bwd (B={w['b']}, K={w['k']} "
-                        f"negatives, {args.loss} loss) + {e} test triples ranked against all entities, heads and tails]",
+    return {"workload": f"synthetic {w['dataset']} ({w['n']} entities, {w['r']} relations) BLP-{w['model']} dim={w['d']}: {c} compute_loss "
+                        f"fwd+bwd (B={w['b']}, K={w['k']} negatives, {args.loss} loss) + one pass over the {c * e} test triples, each "
+                        f"ranked against all entities (heads and tails)",
             "entities": w["n"], "relations": w["r"], "dim": w["d"], "rel_model": w["model"], "loss": args.loss,
-            "train_batch": w["b"], "negatives": w["k"], "eval_triples_per_substep": e, "substeps_per_step": c,
-            "eval_mode": args.mode, "test_triples": f"{w['t']} synthetic triples in relation order (sorted once per evaluation)",
+            "train_batch": w["b"], "negatives": w["k"], "train_steps_per_step": c, "eval_triples_per_step": c * e,
+            "eval_mode": args.mode,
+            "test_triples": f"{w['t']} synthetic triples in relation-aligned order (sorted and padded once per evaluation set)",
             "triples_per_step": step_triples(w, e),
             "l2": "flushed between timed steps (256 MiB write); inside a step the 7.4 MB table is L2-resident by design",
             "parallelism": "replicas: train sub-batches independent, eval queries sharded over the GPUs, table replicated "
@@ -400,9 +402,10 @@ def time_calls(fn, reps, warm=2):
 # executed = mean of head and tail prediction (head prediction cannot pre-fold (candidate op relation) bit-exactly)
 ALG_OPS = {"transe": 2.0, "distmult": 2.0, "complex": 4.0, "simple": 2.5}
 EXEC_OPS = {"transe": 2.5, "distmult": 2.5, "complex": 5.0, "simple": 2.5}
+EXEC_OPS_ALIGNED_TRANSE = 2.125   # relation-aligned order: fl(candidate + r) once per 4 head queries -> (1 + 4 * 2) / 4 and 2
 
 
-def sweep_roofline(model, mode, n, d, q_per_launch, kern_s, peaks, fp32_peak, hbm_peak, extra=None):
+def sweep_roofline(model, mode, n, d, q_per_launch, kern_s, peaks, fp32_peak, hbm_peak, extra=None, exec_ops=None):
     """Roofline block of one sweep launch ranking q_per_launch queries against n candidates, bound = the binding one."""
     alg_bytes = n * d * 4 + (q_per_launch // 2) * 3 * d * 4 + q_per_launch * 12
     out = {"kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
@@ -419,11 +422,11 @@ def sweep_roofline(model, mode, n, d, q_per_launch, kern_s, peaks, fp32_peak, hb
         peak = fp32_peak or 148 * 128 * 1.965e9 / 1e12
         out.update({"bound": "fp32_alu", "achieved": ops_alg / kern_s / 1e12, "peak": peak, "unit": "T lane-op/s",
                     "frac": ops_alg / kern_s / 1e12 / peak,
-                    "frac_executed_ops": q_per_launch * n * d * EXEC_OPS[model] / kern_s / 1e12 / peak,
+                    "frac_executed_ops": q_per_launch * n * d * (exec_ops or EXEC_OPS[model]) / kern_s / 1e12 / peak,
                     "peak_source": "blp_pipe_probe FADD / FADD2 issue rate measured in this run" if fp32_peak
                                    else "nominal 148 SM x 128 lanes x 1.965 GHz",
                     "note": f"exact-order fp32: {ALG_OPS[model]:g} lane-ops per (query, candidate, dim) algorithmic (SURVEY 8d), "
-                            f"{EXEC_OPS[model]:g} executed (head prediction cannot pre-fold the relation bit-exactly)"})
+                            f"{(exec_ops or EXEC_OPS[model]):g} executed (head prediction cannot pre-fold the relation bit-exactly)"})
     if extra:
         out.update(extra)
     return out
@@ -698,24 +701,41 @@ def main_b200(args):
 
     chunks = [triples[(torch.arange(c * e, (c + 1) * e, device=dev) % t)].contiguous() for c in range(C)]
     fast_ws = ops.fast_table(ent) if args.mode == "fast" else None
-    # pre-validated sweep for E triples per call: ONE ctypes call and (exact mode) ONE kernel launch per sub-step
-    plan = blp_b200.RankSweepPlan(args.model, ent, rel_w, e, mode=args.mode, fast_table=fast_ws)
+    whole_sweep = args.mode == "exact"
+    if whole_sweep:
+        # exact mode: the whole evaluation set in ONE launch per step; relation-aligned order, prepared once per set
+        eval_set = blp_b200.AlignedTriples(triples[:C * e].contiguous()) if args.model == "transe" else triples[:C * e].contiguous()
+        plan = None
+    else:
+        # tensor-core mode: pre-validated sweep for E triples per call (fold + sweep + metrics launches)
+        plan = blp_b200.RankSweepPlan(args.model, ent, rel_w, e, mode=args.mode, fast_table=fast_ws)
 
-    # CUDA events bracketing the dominant kernel (the eval sweep) of every timed sub-step, on its own stream
-    prof = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps * C)]
+    # CUDA events bracketing the dominant kernel (the eval sweep) of every timed launch, on its own stream
+    n_prof = steps * (1 if whole_sweep else C)
+    prof = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_prof)]
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a_, b_ in prof + step_ev:          # materialise the cudaEvent_t handles
         a_.record(); b_.record()
 
+    def set_prof(idx):
+        pa, pb = prof[idx]
+        lib.blp_profile_events(1, ctypes.c_void_p(pa.cuda_event), ctypes.c_void_p(pb.cuda_event))
+
     def step(i, timed_index=None):
         loss = out = None
+        if whole_sweep:
+            # the sweep is enqueued first: the launch-bound training sub-steps are then issued while the GPU ranks
+            if timed_index is not None:
+                set_prof(timed_index)
+            out = blp_b200.rank_sweep(args.model, ent, rel_w, eval_set, sort_by_relation=False)
+            launches["n"] += out["launches"]
         for c in range(C):
             loss = train_step()
-            if timed_index is not None:
-                pa, pb = prof[timed_index * C + c]
-                lib.blp_profile_events(1, ctypes.c_void_p(pa.cuda_event), ctypes.c_void_p(pb.cuda_event))
-            out = plan(chunks[c])
-            launches["n"] += out["launches"]
+            if not whole_sweep:
+                if timed_index is not None:
+                    set_prof(timed_index * C + c)
+                out = plan(chunks[c])
+                launches["n"] += out["launches"]
         return loss, out
 
     def barrier():
@@ -772,6 +792,16 @@ def main_b200(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    h_eval = pin(test_triples[:C * e])
+    if whole_sweep:
+        h2d_step = C * (h_ent_embs.numel() * 4 + h_rels.numel() * 8 + h_neg.numel() * 8) + h_eval.numel() * 8
+        d2h_step = C * 4 + 4 * 8
+    else:
+        h2d_step, d2h_step = C * h2d_sub, C * d2h_sub
+    dev_eval = torch.empty_like(h_eval, device=dev)
+    step_sums = torch.empty(4, dtype=torch.float64).pin_memory()
+    eval_consumed = [None]
+
     def e2e_prefetch(j):
         slot = stage[j & 1]
         with torch.cuda.stream(copy_stream):
@@ -779,7 +809,8 @@ def main_b200(args):
             slot["ent"].copy_(h_ent_embs, non_blocking=True)
             slot["rels"].copy_(h_rels, non_blocking=True)
             slot["neg"].copy_(h_neg, non_blocking=True)
-            slot["tr"].copy_(h_triples[j % C], non_blocking=True)
+            if not whole_sweep:
+                slot["tr"].copy_(h_triples[j % C], non_blocking=True)
             ready[j & 1].record(copy_stream)
 
     def e2e_issue(j, first):
@@ -796,30 +827,59 @@ def main_b200(args):
             rel_w.grad = None
             loss = model.compute_loss(x, slot["rels"], slot["neg"].transpose(0, 1))
             loss.backward()
-        out = plan(slot["tr"])
+        out = plan(slot["tr"]) if not whole_sweep else None
         consumed[j & 1].record(main)
-        # D2H: the loss scalar (train.py:352) + the 4 fp64 metric accumulators (train.py:154-157)
+        # D2H: the loss scalar (train.py:352) [+ the 4 fp64 metric accumulators (train.py:154-157) per call]
         host_loss[j & 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        host_sums[j & 1].copy_(out["sums"], non_blocking=True)
+        if out is not None:
+            host_sums[j & 1].copy_(out["sums"], non_blocking=True)
         landed[j & 1].record()
 
     def e2e_read(j):
         landed[j & 1].synchronize()
         return float(host_loss[j & 1][0]), float(host_sums[j & 1][0]) / (2 * e)
 
-    def e2e_run(n_sub):
-        last = None
-        for j in range(n_sub):
-            e2e_issue(j, first=(j == 0))
-            if j > 0:
-                last = e2e_read(j - 1)
-        return e2e_read(n_sub - 1) if n_sub else last
+    def e2e_copy_eval():
+        """The evaluation set of the NEXT step crosses PCIe on the copy stream while this step computes."""
+        with torch.cuda.stream(copy_stream):
+            if eval_consumed[0] is not None:
+                copy_stream.wait_event(eval_consumed[0])           # the staging buffer has been gathered from
+            dev_eval.copy_(h_eval, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
 
-    e2e_run(min(warmup, 3) * C)
+    def e2e_run(n_steps):
+        last = None
+        eval_ready = e2e_copy_eval() if (whole_sweep and n_steps) else None
+        for s_i in range(n_steps):
+            if whole_sweep:
+                main = torch.cuda.current_stream()
+                main.wait_event(eval_ready)
+                ev_set = eval_set.load(dev_eval) if isinstance(eval_set, blp_b200.AlignedTriples) else eval_set.copy_(dev_eval)
+                eval_consumed[0] = torch.cuda.Event()
+                eval_consumed[0].record(main)
+                out = blp_b200.rank_sweep(args.model, ent, rel_w, ev_set, sort_by_relation=False)
+                step_sums.copy_(out["sums"], non_blocking=True)
+                if s_i + 1 < n_steps:
+                    eval_ready = e2e_copy_eval()
+            for c in range(C):
+                j = s_i * C + c
+                e2e_issue(j, first=(j == 0))
+                if j > 0:
+                    last = e2e_read(j - 1)
+        if n_steps:
+            last = e2e_read(n_steps * C - 1)
+            torch.cuda.current_stream().synchronize()
+            if whole_sweep:
+                last = (last[0], float(step_sums[0]) / (2 * C * e))
+        return last
+
+    e2e_run(min(warmup, 3))
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    last = e2e_run(steps * C)
+    last = e2e_run(steps)
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
@@ -860,8 +920,13 @@ def main_b200(args):
     kname = f"{'fast_sweep_kernel' if args.mode == 'fast' else 'sweep_kernel'}<{args.model}>"
     share = sum(kern_ms) / sum(step_ms)
     roofline = {"kernel": kname}
-    roofline.update(sweep_roofline(args.model, args.mode, n, d, 2 * e, kern_s, peaks, fp32_peak, hbm_peak))
-    roofline["traffic"] = ncu_traffic(f"{kname}|{args.dataset}|E{e}|{args.mode}")
+    q_launch = 2 * C * e if whole_sweep else 2 * e                 # real queries ranked by one sweep launch
+    roofline.update(sweep_roofline(args.model, args.mode, n, d, q_launch, kern_s, peaks, fp32_peak, hbm_peak,
+                                   exec_ops=EXEC_OPS_ALIGNED_TRANSE if (whole_sweep and args.model == "transe") else None))
+    if whole_sweep and args.model == "transe":
+        roofline["launch"] = (f"{eval_set.num_padded} entries per launch: {eval_set.num_triples} test triples in relation-aligned order + "
+                              f"{eval_set.num_padded - eval_set.num_triples} padding entries (computed, not counted)")
+    roofline["traffic"] = ncu_traffic(f"{kname}|{args.dataset}|E{C * e if whole_sweep else e}|{args.mode}")
     roofline["kernel_share_of_step"] = share
     roofline["launches_timed"] = len(kern_ms)
     roofline["timed"] = "CUDA events around every sweep launch of the timed region (blp_profile_events, launching stream)"
@@ -897,7 +962,7 @@ def main_b200(args):
         "dtype": "f32" if args.mode == "exact" else "f16x3 split of f32 (fp32 accumulate; train step f32)", "data": "synthetic",
         "config": config_dict(args, w, e, world),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_sub * C, "d2h_bytes_per_step": d2h_sub * C,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                 "ms_per_step": e2e_ms / steps, "last_loss": last[0], "last_mrr": last[1]},
         "gpu_launches": timed_launches,
         "roofline": roofline, "cpu_baseline": cpu,

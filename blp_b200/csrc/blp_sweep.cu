@@ -42,7 +42,7 @@
 #define BLP_UNROLL_CC 8
 #endif
 #ifndef BLP_UNROLL_CC_SHARED
-#define BLP_UNROLL_CC_SHARED 4
+#define BLP_UNROLL_CC_SHARED 8
 #endif
 
 namespace blp {
@@ -297,8 +297,8 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
 
     if (MODEL == BLP_MODEL_TRANSE) {
         // strictly sequential L1 accumulation, natural order
-        // the kernel holds two copies of this loop nest (shared / per-query relation); the shared one is unrolled
-        // less so that the hot loop bodies stay inside the instruction cache (ncu: stall_no_instructions)
+        // the kernel holds two copies of this loop nest (shared / per-query relation); only one of them is hot at any
+        // time (the choice is per triple group), so both can be unrolled fully without instruction-cache thrash
         constexpr int kUnrollCC = SHARED_R ? BLP_UNROLL_CC_SHARED : BLP_UNROLL_CC;
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb)
@@ -702,18 +702,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         int cgt[C::SQ], cge[C::SQ];
 #pragma unroll
         for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
-        // TransE, mixed role: do this slot's head-prediction triples share one relation row?  (warp-uniform)
+        // TransE, mixed role: do the head-prediction triples of EVERY slot of this group share one relation row per slot?
+        // Then w = fl(candidate + r) is computed once per slot (score_tile<..., SHARED_R>).  The decision is taken per
+        // group, not per slot, so that all warps of the CTA run the same loop nest at any time: the two nests are
+        // ~20 KB of code each and evict each other from the instruction cache when both are hot (measured: 456 us
+        // instead of 284 / 314 us per 1,024-triple launch).  rank_sweep(sort_by_relation=True) pads every relation's run
+        // to a multiple of 4 triples, which makes every group uniform.
 #ifndef BLP_SHARED_R
 #define BLP_SHARED_R 1
 #endif
         bool shared_r = false;
         if (BLP_SHARED_R && MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
-            const long long tr0 = t0 + QM::triple(slot, 0);
-            shared_r = tr0 + C::TQP <= args.b;
-            if (shared_r) {
-                const float *r0 = args.r.row(tr0, kD);
+            shared_r = true;
 #pragma unroll
-                for (int q = 1; q < C::TQP; ++q) shared_r &= args.r.row(tr0 + q, kD) == r0;
+            for (int s_ = 0; s_ < C::NS; ++s_) {
+                const long long tr0 = t0 + QM::triple(s_, 0);
+                if (tr0 >= args.b) continue;                       // slot past the end of the batch: no work
+                bool ok = tr0 + C::TQP <= args.b;
+                const float *r0 = sm.rowp[s_ * C::SQ][2];
+#pragma unroll
+                for (int q = 1; q < C::TQP; ++q) ok &= sm.rowp[s_ * C::SQ + q][2] == r0;
+                shared_r &= ok;
             }
         }
 
@@ -727,9 +736,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
                 f2 sp[C::TQP][C::TC];
                 const TileView<MODEL> tv(&sm.ctile[buf][0], row_off);
-                if (BLP_SHARED_R && QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4 && shared_r)
+#ifndef BLP_FORCE_SHARED
+#define BLP_FORCE_SHARED 0      // timing experiment only: the shared-relation loop nest alone (wrong results unless every slot shares r)
+#endif
+                constexpr bool kCanShare = BLP_SHARED_R && QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4;
+                if (kCanShare && (BLP_FORCE_SHARED || shared_r))
                     score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
-                else if (QM::kMixed) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
+                else if (QM::kMixed && !(kCanShare && BLP_FORCE_SHARED)) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else if (QM::is_head(slot, 0)) score_tile<MODEL, kRoleHead, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
                 else score_tile<MODEL, kRoleTail, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
 #pragma unroll

@@ -183,8 +183,11 @@ __device__ __forceinline__ float softplus_grad_f(float x) {
     return z / (z + 1.f);
 }
 
+#ifndef BLP_TRAIN_MINB
+#define BLP_TRAIN_MINB 1
+#endif
 template <int MODEL, int NCH2, int ILP, bool GRAD>
-__global__ void __launch_bounds__(kTrainThreads) train_kernel(const TrainArgs a) {
+__global__ void __launch_bounds__(kTrainThreads, (NCH2 <= 2 ? BLP_TRAIN_MINB : 1)) train_kernel(const TrainArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long b = blockIdx.x / a.slices;
     const int slice = blockIdx.x % a.slices;
@@ -387,8 +390,11 @@ template <int MODEL>
 static int dispatch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
     const int P = TM<MODEL>::kHalves ? a.d / 2 : a.d;
     const int need = (P + 63) / 64;
-    if (need <= 1) return launch_train<MODEL, 1, 4>(a, grad, st);
-    if (need <= 2) return launch_train<MODEL, 2, 4>(a, grad, st);
+#ifndef BLP_TRAIN_ILP
+#define BLP_TRAIN_ILP 4
+#endif
+    if (need <= 1) return launch_train<MODEL, 1, BLP_TRAIN_ILP>(a, grad, st);
+    if (need <= 2) return launch_train<MODEL, 2, BLP_TRAIN_ILP>(a, grad, st);
     if (need <= 4) return launch_train<MODEL, 4, 2>(a, grad, st);
     if (need <= 6) return launch_train<MODEL, 6, 2>(a, grad, st);
     if (need <= 12) return launch_train<MODEL, 12, 1>(a, grad, st);
@@ -453,8 +459,11 @@ extern "C" int blp_train_loss(int model, int loss, const float *ent_embs, const 
     int slices = 1;
     while (slices < 8 && b * slices * 2 <= 160 && k / (slices * 2) >= 64) slices *= 2;
     {
-        const char *e = getenv("BLP_TRAIN_SLICES");       // tuning aid
-        if (e && atoi(e) >= 1 && atoi(e) <= 8) slices = atoi(e);
+        static const int forced = []() {                  // tuning aid, read once (not per step)
+            const char *e = getenv("BLP_TRAIN_SLICES");
+            return (e && atoi(e) >= 1 && atoi(e) <= 8) ? atoi(e) : 0;
+        }();
+        if (forced) slices = forced;
     }
     a.slices = slices;
     switch (model) {

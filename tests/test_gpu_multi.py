@@ -75,3 +75,42 @@ def test_nccl_sharded_sweep_equals_single_gpu(model, mode, cuda_device):
         # something within the tie band of the exact ranks -- on this tiny table they coincide except for near-ties
         diff = np.abs(ret["gt"].astype(np.int64) - single["gt"].cpu().numpy().astype(np.int64))
         assert diff.max() <= 2 and (diff > 0).mean() < 0.05
+
+
+@pytest.mark.parametrize("model,loss", [("transe", "margin"), ("complex", "nll")])
+def test_dataparallel_threads_compute_loss_concurrently(model, loss, cuda_device):
+    """The reference's only multi-GPU mechanism (train.py:329-330): torch.nn.DataParallel runs forward() from one Python
+    thread per device, concurrently, each on its sub-batch with LOCAL in-batch negatives (data.py:289-298, repeats =
+    number of devices).  The C ABI must be re-entrant (thread-local error / launch state, per-(device, stream)
+    workspaces, device taken from the tensors): per-replica losses and the reduced gradients must equal the oracle's."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import c_oracle
+    n_dev, b_per, k, d, n_ent, n_rel = 2, 24, 40, 128, 300, 9
+    torch.manual_seed(5)
+    m = blp_b200.TransductiveLinkPrediction(d, model, loss, n_ent, n_rel, 1e-3 if model == "complex" else 0)
+    dp = torch.nn.DataParallel(m, device_ids=list(range(n_dev))).to(torch.device("cuda", 0))
+    g = torch.Generator().manual_seed(6)
+    pos_pairs = torch.randint(0, n_ent, (n_dev * b_per, 2), generator=g)
+    rels = torch.randint(0, n_rel, (n_dev * b_per, 1), generator=g)
+    # data.py:289-298: indices local to each device's sub-batch of b_per pairs
+    neg_idx = torch.cat([blp_b200.get_negative_sampling_indices(b_per, k, device=cuda_device, seed=7 + i).contiguous().cpu()
+                         for i in range(n_dev)])
+    for it in range(3):                                  # repeated steps: replicas are rebuilt, threads re-enter
+        dp.zero_grad()
+        per_replica = dp(pos_pairs.to(cuda_device), rels.to(cuda_device), neg_idx.to(cuda_device))
+        assert per_replica.shape == (n_dev,)
+        per_replica.mean().backward()                    # train.py:343-346
+    ent_w, rel_w = m.ent_emb.weight.detach().cpu(), m.rel_emb.weight.detach().cpu()
+    want_grad_rel = np.zeros((n_rel, d), np.float64)
+    for i in range(n_dev):
+        sl = slice(i * b_per, (i + 1) * b_per)
+        embs = ent_w[pos_pairs[sl]]
+        if model == "transe":
+            embs = torch.nn.functional.normalize(embs, dim=-1)
+        co = c_oracle.train_loss(model, loss, embs.numpy(), rel_w[rels[sl, 0]].numpy(), neg_idx[sl].numpy(),
+                                 float(m.regularizer))
+        assert abs(float(per_replica[i]) - float(co["loss"])) <= 1e-5 * abs(float(co["loss"])), i
+        np.add.at(want_grad_rel, rels[sl, 0].numpy(), co["grad_rel"].astype(np.float64) / n_dev)
+    got = m.rel_emb.weight.grad.cpu().numpy()
+    assert np.abs(got - want_grad_rel).max() <= 2e-5 * np.abs(want_grad_rel).max()

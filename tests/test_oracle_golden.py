@@ -104,3 +104,58 @@ def test_np_oracle_normalize_bits():
     g = golden("normalize")
     for d in (128, 300, 768, 100):
         assert np.array_equal(np_oracle.l2_normalize_rows(g[f"x_{d}"]), g[f"y_{d}"]), d
+
+
+@pytest.mark.parametrize("model", ("transe", "distmult", "complex", "simple"))
+def test_torch_port_equals_reference(model):
+    """oracle/torch_port.py (the CPU arm's fallback when oracle/_ref is absent) against the reference's OWN functions
+    (imported from /root/reference, or byte-compiled under oracle/_ref): compute_loss forward + backward with the
+    reference sampler's strided neg_idx (models.py:51-70), and the eval statements train.py:141-153 / 164-167 --
+    bit for bit (single-threaded, so the mean reductions are order-stable too)."""
+    import torch
+    from oracle import ref_loader, torch_port
+    if ref_loader.available() is None:
+        pytest.skip("reference modules not available (python oracle/build_ref.py where /root/reference is mounted)")
+    mods = ref_loader.load(("models", "utils", "data"))
+    ref_models, ref_utils, ref_data = mods["models"], mods["utils"], mods["data"]
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.manual_seed(3)
+        b, k, d, n, n_rel = 16, 24, 128, 300, 7
+        for loss in ("margin", "nll"):
+            reg = 1e-3 if model == "complex" else 0
+            m = ref_models.TransductiveLinkPrediction(d, model, loss, n, n_rel, reg)
+            pairs = torch.randint(0, n, (b, 2))
+            rels = torch.randint(0, n_rel, (b, 1))
+            neg_idx = ref_data.get_negative_sampling_indices(b, k)            # strided view, data.py:78-79
+            x_ref = m.encode(pairs).detach().clone().requires_grad_(True)
+            want = m.compute_loss(x_ref, rels, neg_idx)
+            want.backward()
+            x = x_ref.detach().clone().requires_grad_(True)
+            w = m.rel_emb.weight.detach().clone().requires_grad_(True)
+            got = torch_port.batch_loss(model, loss, x, w[rels[:, 0]], neg_idx, reg)
+            got.backward()
+            assert torch.equal(got.detach(), want.detach()), (model, loss)
+            assert torch.equal(x.grad, x_ref.grad) and torch.equal(w.grad, m.rel_emb.weight.grad)
+        # eval statements, raw and filtered
+        ent_emb = m.encode(torch.arange(n)).detach().unsqueeze(0)
+        heads, tails = torch.randint(0, n, (b, 1)), torch.randint(0, n, (b, 1))
+        rel_embs = m.rel_emb(rels).detach()
+        k_values = torch.tensor([[1, 3, 10]])
+        with torch.no_grad():
+            head_embs, tail_embs = ent_emb.squeeze()[heads], ent_emb.squeeze()[tails]
+            pred = torch.cat((m.score_fn(ent_emb, tail_embs, rel_embs), m.score_fn(head_embs, ent_emb, rel_embs)))
+            true = torch.cat((heads, tails))
+            recip, hits = ref_utils.get_metrics(pred, true, k_values)
+            mask = torch.rand(2 * b, n) < 0.03
+            mask[torch.arange(2 * b), true[:, 0]] = False
+            pred_f = pred.clone()
+            pred_f[mask] = pred_f.min() - 1.0
+            recip_f, hits_f = ref_utils.get_metrics(pred_f, true, k_values)
+        out = torch_port.eval_batch(model, ent_emb, heads, tails, rel_embs, k_values, filter_mask=mask)
+        assert torch.equal(out["recip"], recip) and torch.equal(out["hits"], hits)
+        assert torch.equal(out["recip_f"], recip_f) and torch.equal(out["hits_f"], hits_f)
+        assert torch.equal(out["pred"], pred_f)
+    finally:
+        torch.set_num_threads(threads)

@@ -402,7 +402,8 @@ def time_calls(fn, reps, warm=2):
 # executed = mean of head and tail prediction (head prediction cannot pre-fold (candidate op relation) bit-exactly)
 ALG_OPS = {"transe": 2.0, "distmult": 2.0, "complex": 4.0, "simple": 2.5}
 EXEC_OPS = {"transe": 2.5, "distmult": 2.5, "complex": 5.0, "simple": 2.5}
-EXEC_OPS_ALIGNED_TRANSE = 2.125   # relation-aligned order: fl(candidate + r) once per 4 head queries -> (1 + 4 * 2) / 4 and 2
+# relation-aligned order: the first rounding of head prediction once per 4 head queries, e.g. TransE ((1 + 4 * 2) / 4 + 2) / 2
+EXEC_OPS_ALIGNED = {"transe": 2.125, "distmult": 2.125, "complex": 4.25, "simple": 2.3125}
 
 
 def sweep_roofline(model, mode, n, d, q_per_launch, kern_s, peaks, fp32_peak, hbm_peak, extra=None, exec_ops=None):
@@ -560,16 +561,27 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
         ent, rel = w["ent"].to(dev), w["rel"].to(dev)
         tr = w["triples"][torch.argsort(w["triples"][:, 2], stable=True)].contiguous()
         e = min(e, w["t"])
-        chunks = [tr[torch.arange(c * e, (c + 1) * e) % w["t"]].contiguous().to(dev) for c in range(max(1, w["t"] // e))]
-        ft = ops.fast_table(ent) if mode == "fast" else None
-        plan = blp_b200.RankSweepPlan(model, ent, rel, e, mode=mode, fast_table=ft)
         state = {"i": 0, "launches": 0}
+        exec_ops = None
+        if mode == "exact" and e == w["t"]:
+            # the whole evaluation set in one launch, relation-aligned order prepared once (like the headline step)
+            aligned = blp_b200.AlignedTriples(tr.to(dev))
+            exec_ops = EXEC_OPS_ALIGNED.get(model)
 
-        def call():
-            out = plan(chunks[state["i"] % len(chunks)])
-            state["i"] += 1
-            state["launches"] = out["launches"]
-            return out
+            def call():
+                out = blp_b200.rank_sweep(model, ent, rel, aligned, sort_by_relation=False)
+                state["launches"] = out["launches"]
+                return out
+        else:
+            chunks = [tr[torch.arange(c * e, (c + 1) * e) % w["t"]].contiguous().to(dev) for c in range(max(1, w["t"] // e))]
+            ft = ops.fast_table(ent) if mode == "fast" else None
+            plan = blp_b200.RankSweepPlan(model, ent, rel, e, mode=mode, fast_table=ft)
+
+            def call():
+                out = plan(chunks[state["i"] % len(chunks)])
+                state["i"] += 1
+                state["launches"] = out["launches"]
+                return out
         ms = time_calls(call, reps=max(3, min(50, int(200 / max(1, e // 64)))), warm=2)
         out = call()
         torch.cuda.synchronize()
@@ -578,7 +590,7 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
                "ms_per_call": ms, "launches_per_call": state["launches"], "scores_per_s": 2 * e * w["n"] / (ms * 1e-3),
                "sweep_s_all_test_triples": ms * 1e-3 * w["t"] / e, "mrr": float(out["sums"][0]) / (2 * e)}
         leg["roofline"] = sweep_roofline(model, mode, w["n"], w["d"], 2 * e, ms * 1e-3, peaks, fp32_peak, hbm_peak,
-                                         {"timed": "whole call (all launches of the call), back to back"})
+                                         {"timed": "whole call (all launches of the call), back to back"}, exec_ops=exec_ops)
         legs[name] = leg
 
     # one call per evaluation set, like the headline step (FB15k-237: 20,480 test triples, WN18RR: 3,136)
@@ -705,7 +717,7 @@ def main_b200(args):
     whole_sweep = args.mode == "exact"
     if whole_sweep:
         # exact mode: the whole evaluation set in ONE launch per step; relation-aligned order, prepared once per set
-        eval_set = blp_b200.AlignedTriples(triples[:C * e].contiguous()) if args.model == "transe" else triples[:C * e].contiguous()
+        eval_set = blp_b200.AlignedTriples(triples[:C * e].contiguous())
         plan = None
     else:
         # tensor-core mode: pre-validated sweep for E triples per call (fold + sweep + metrics launches)
@@ -780,9 +792,10 @@ def main_b200(args):
     h_triples = [pin(test_triples[torch.arange(c * e, (c + 1) * e) % t]) for c in range(C)]
     h2d_sub = h_ent_embs.numel() * 4 + h_rels.numel() * 8 + h_neg.numel() * 8 + h_triples[0].numel() * 8
     d2h_sub = 4 + 4 * 8
-    # results are read on the host one sub-step behind the GPU (two pinned result slots), like a training loop that logs
-    # the previous step's loss while the next step is already queued: every sub-step still does its H2D and its D2H
-    host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # results are read on the host one STEP behind the GPU (two pinned result slots), like a training loop that logs the
+    # previous step's losses and metrics while the next step is already queued: every step still does all of its H2D
+    # and D2H copies inside the timed region
+    host_loss = [torch.empty(C, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_sums = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     landed = [torch.cuda.Event(), torch.cuda.Event()]
     # host -> device prefetch, the way a pinned-memory DataLoader feeds a training loop: the inputs of sub-step j + 1 cross
@@ -800,7 +813,6 @@ def main_b200(args):
     else:
         h2d_step, d2h_step = C * h2d_sub, C * d2h_sub
     dev_eval = torch.empty_like(h_eval, device=dev)
-    step_sums = torch.empty(4, dtype=torch.float64).pin_memory()
     eval_consumed = [None]
 
     def e2e_prefetch(j):
@@ -831,14 +843,14 @@ def main_b200(args):
         out = plan(slot["tr"]) if not whole_sweep else None
         consumed[j & 1].record(main)
         # D2H: the loss scalar (train.py:352) [+ the 4 fp64 metric accumulators (train.py:154-157) per call]
-        host_loss[j & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        s_i, c = divmod(j, C)
+        host_loss[s_i & 1][c:c + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         if out is not None:
-            host_sums[j & 1].copy_(out["sums"], non_blocking=True)
-        landed[j & 1].record()
+            host_sums[s_i & 1].copy_(out["sums"], non_blocking=True)
 
-    def e2e_read(j):
-        landed[j & 1].synchronize()
-        return float(host_loss[j & 1][0]), float(host_sums[j & 1][0]) / (2 * e)
+    def e2e_read(s_i):
+        landed[s_i & 1].synchronize()
+        return float(host_loss[s_i & 1][C - 1]), float(host_sums[s_i & 1][0]) / (2 * (C * e if whole_sweep else e))
 
     def e2e_copy_eval():
         """The evaluation set of the NEXT step crosses PCIe on the copy stream while this step computes."""
@@ -857,23 +869,21 @@ def main_b200(args):
             if whole_sweep:
                 main = torch.cuda.current_stream()
                 main.wait_event(eval_ready)
-                ev_set = eval_set.load(dev_eval) if isinstance(eval_set, blp_b200.AlignedTriples) else eval_set.copy_(dev_eval)
+                ev_set = eval_set.load(dev_eval)
                 eval_consumed[0] = torch.cuda.Event()
                 eval_consumed[0].record(main)
                 out = blp_b200.rank_sweep(args.model, ent, rel_w, ev_set, sort_by_relation=False)
-                step_sums.copy_(out["sums"], non_blocking=True)
+                host_sums[s_i & 1].copy_(out["sums"], non_blocking=True)
                 if s_i + 1 < n_steps:
                     eval_ready = e2e_copy_eval()
             for c in range(C):
                 j = s_i * C + c
                 e2e_issue(j, first=(j == 0))
-                if j > 0:
-                    last = e2e_read(j - 1)
+            landed[s_i & 1].record()
+            if s_i > 0:
+                last = e2e_read(s_i - 1)
         if n_steps:
-            last = e2e_read(n_steps * C - 1)
-            torch.cuda.current_stream().synchronize()
-            if whole_sweep:
-                last = (last[0], float(step_sums[0]) / (2 * C * e))
+            last = e2e_read(n_steps - 1)
         return last
 
     e2e_run(min(warmup, 3))
@@ -923,8 +933,8 @@ def main_b200(args):
     roofline = {"kernel": kname}
     q_launch = 2 * C * e if whole_sweep else 2 * e                 # real queries ranked by one sweep launch
     roofline.update(sweep_roofline(args.model, args.mode, n, d, q_launch, kern_s, peaks, fp32_peak, hbm_peak,
-                                   exec_ops=EXEC_OPS_ALIGNED_TRANSE if (whole_sweep and args.model == "transe") else None))
-    if whole_sweep and args.model == "transe":
+                                   exec_ops=EXEC_OPS_ALIGNED.get(args.model) if whole_sweep else None))
+    if whole_sweep:
         roofline["launch"] = (f"{eval_set.num_padded} entries per launch: {eval_set.num_triples} test triples in relation-aligned order + "
                               f"{eval_set.num_padded - eval_set.num_triples} padding entries (computed, not counted)")
     roofline["traffic"] = ncu_traffic(f"{kname}|{args.dataset}|E{C * e if whole_sweep else e}|{args.mode}")

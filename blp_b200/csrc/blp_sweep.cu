@@ -362,8 +362,37 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
                     const float4 v = tv.load(i, off >> 2);
                     e[i][0] = v.x; e[i][1] = v.y; e[i][2] = v.z; e[i][3] = v.w;
                 }
+                constexpr int kHeadPairs = (SHARED_R && ROLE == kRoleMixed) ? TQP / 2 : 0;
+                if (kHeadPairs > 0) {
+                    // shared relation (relation-aligned order): fl(e * r) -- the first rounding of models.py:227 when the
+                    // candidate plays `heads` -- once per (candidate, position) for all head pairs of the slot
+                    const Q4 r4 = ldq4(qv, 0, 0, off);
+                    const f2 rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                    f2 w[TC][4];
 #pragma unroll
-                for (int q = 0; q < TQP; ++q) {
+                    for (int k = 0; k < 4; ++k) {
+                        float r_lo, r_hi;
+                        unpack2(rv[k], r_lo, r_hi);
+#pragma unroll
+                        for (int i = 0; i < TC; ++i) w[i][k] = dup2(fmul(e[i][k], r_lo));
+                    }
+#pragma unroll
+                    for (int q = 0; q < kHeadPairs; ++q) {
+                        const Q4 v1 = ldq4(qv, q, 1, off);
+                        const f2 v1v[4] = {v1.x, v1.y, v1.z, v1.w};
+                        f2 chain[TC];
+#pragma unroll
+                        for (int i = 0; i < TC; ++i) chain[i] = mul2(w[i][0], v1v[0], nz);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k)
+#pragma unroll
+                            for (int i = 0; i < TC; ++i) chain[i] = add2(chain[i], mul2(w[i][k], v1v[k], nz));
+#pragma unroll
+                        for (int i = 0; i < TC; ++i) c[q][i] = add2(c[q][i], chain[i]);
+                    }
+                }
+#pragma unroll
+                for (int q = kHeadPairs; q < TQP; ++q) {
                     const Q4 v0 = ldq4(qv, q, 0, off);
                     const Q4 v1 = HEAD_PRED ? ldq4(qv, q, 1, off) : q4_zero();
                     const f2 v0v[4] = {v0.x, v0.y, v0.z, v0.w}, v1v[4] = {v1.x, v1.y, v1.z, v1.w};
@@ -401,8 +430,65 @@ __device__ __forceinline__ void score_tile(const TileView<MODEL> tv, const float
                     elo[i] = tv.load(i, off >> 2);
                     ehi[i] = tv.load(i, (off >> 2) + 16);
                 }
+                constexpr int kHeadPairsH = (SHARED_R && ROLE == kRoleMixed) ? TQP / 2 : 0;
+                if (kHeadPairsH > 0) {
+                    // shared relation: the products of the candidate with the relation -- ComplEx rr*hr, rr*hi, ri*hr, ri*hi
+                    // (models.py:235-238), SimplE hh*ra (models.py:247) -- once per (candidate, position) for all head pairs
+                    const Q4 ra4 = ldq4(qv, 0, 0, off);
+                    const Q4 rb4 = (MODEL == BLP_MODEL_COMPLEX) ? ldq4(qv, 0, 0, 64 + off) : q4_zero();
+                    const f2 rav[4] = {ra4.x, ra4.y, ra4.z, ra4.w}, rbv[4] = {rb4.x, rb4.y, rb4.z, rb4.w};
+                    float rr[4], ri[4];
 #pragma unroll
-                for (int q = 0; q < TQP; ++q) {
+                    for (int x = 0; x < 4; ++x) {
+                        float dummy;
+                        unpack2(rav[x], rr[x], dummy);
+                        unpack2(rbv[x], ri[x], dummy);
+                    }
+                    Q4 hv1lo[kHeadPairsH > 0 ? kHeadPairsH : 1], hv1hi[kHeadPairsH > 0 ? kHeadPairsH : 1];
+#pragma unroll
+                    for (int q = 0; q < kHeadPairsH; ++q) {
+                        // ComplEx: v1 = (tr | ti); SimplE: tt lives in v0's second half, th*rb in v1's first half
+                        hv1lo[q] = ldq4(qv, q, 1, off);
+                        hv1hi[q] = (MODEL == BLP_MODEL_COMPLEX) ? ldq4(qv, q, 1, 64 + off) : ldq4(qv, q, 0, 64 + off);
+                    }
+#pragma unroll
+                    for (int i = 0; i < TC; ++i) {
+                        const float el[4] = {elo[i].x, elo[i].y, elo[i].z, elo[i].w}, eh[4] = {ehi[i].x, ehi[i].y, ehi[i].z, ehi[i].w};
+                        f2 wa[4], wb[4], wc[4], wd[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            wa[x] = dup2(fmul(rr[x], el[x]));                   // ComplEx rr*hr, SimplE hh*ra
+                            if (MODEL == BLP_MODEL_COMPLEX) {
+                                wb[x] = dup2(fmul(rr[x], eh[x]));               // rr*hi
+                                wc[x] = dup2(fmul(ri[x], el[x]));               // ri*hr
+                                wd[x] = dup2(fmul(ri[x], eh[x]));               // ri*hi
+                            } else {
+                                wb[x] = dup2(eh[x]);                            // ht
+                                wc[x] = wd[x] = 0ull;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < kHeadPairsH; ++q) {
+                            const f2 t_lo[4] = {hv1lo[q].x, hv1lo[q].y, hv1lo[q].z, hv1lo[q].w};
+                            const f2 t_hi[4] = {hv1hi[q].x, hv1hi[q].y, hv1hi[q].z, hv1hi[q].w};
+                            f2 pp[4];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                if (MODEL == BLP_MODEL_COMPLEX) {
+                                    f2 p = add2(mul2(wa[x], t_lo[x], nz), mul2(wb[x], t_hi[x], nz));
+                                    p = add2(p, mul2(wc[x], t_hi[x], nz));
+                                    pp[x] = sub2(p, mul2(wd[x], t_lo[x], nz));
+                                } else {   // (hh*ra)*tt + (th*rb)*ht : t_hi = tt, t_lo = th*rb
+                                    pp[x] = add2(mul2(wa[x], t_hi[x], nz), mul2(t_lo[x], wb[x], nz));
+                                }
+                            }
+                            const f2 cc = add2(c[q][i], add2(pp[0], pp[1]));
+                            c[q][i] = add2(cc, add2(pp[2], pp[3]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = kHeadPairsH; q < TQP; ++q) {
                     const Q4 v0lo = ldq4(qv, q, 0, off);
                     const Q4 v0hi = ldq4(qv, q, 0, 64 + off);
                     const Q4 v1lo = ldq4(qv, q, 1, off);
@@ -702,8 +788,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         int cgt[C::SQ], cge[C::SQ];
 #pragma unroll
         for (int q = 0; q < C::SQ; ++q) cgt[q] = cge[q] = 0;
-        // TransE, mixed role: do the head-prediction triples of EVERY slot of this group share one relation row per slot?
-        // Then w = fl(candidate + r) is computed once per slot (score_tile<..., SHARED_R>).  The decision is taken per
+        // Mixed role: do the head-prediction triples of EVERY slot of this group share one relation row per slot?  Then the
+        // first rounding of head prediction -- fl(candidate + r) for TransE, fl(candidate * r) for the bilinear models --
+        // is computed once per slot (score_tile<..., SHARED_R>).  The decision is taken per
         // group, not per slot, so that all warps of the CTA run the same loop nest at any time: the two nests are
         // ~20 KB of code each and evict each other from the instruction cache when both are hot (measured: 456 us
         // instead of 284 / 314 us per 1,024-triple launch).  rank_sweep(sort_by_relation=True) pads every relation's run
@@ -712,7 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #define BLP_SHARED_R 1
 #endif
         bool shared_r = false;
-        if (BLP_SHARED_R && MODEL == BLP_MODEL_TRANSE && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
+        if (BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
             shared_r = true;
 #pragma unroll
             for (int s_ = 0; s_ < C::NS; ++s_) {
@@ -739,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #ifndef BLP_FORCE_SHARED
 #define BLP_FORCE_SHARED 0      // timing experiment only: the shared-relation loop nest alone (wrong results unless every slot shares r)
 #endif
-                constexpr bool kCanShare = BLP_SHARED_R && QM::kMixed && MODEL == BLP_MODEL_TRANSE && C::TQP >= 2 && C::TC == 4;
+                constexpr bool kCanShare = BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && C::TC == 4;
                 if (kCanShare && (BLP_FORCE_SHARED || shared_r))
                     score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
                 else if (QM::kMixed && !(kCanShare && BLP_FORCE_SHARED)) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);

@@ -80,9 +80,10 @@ class AlignedTriples:
     """Test triples in RELATION-ALIGNED order, prepared once per evaluation set.
 
     The triples are sorted by relation and every relation's run is padded to a multiple of 4 entries with duplicates of
-    its last triple.  The TransE sweep kernel gives 4 consecutive triples to one warp; when they share the relation,
-    fl(candidate + r) -- the first rounding of models.py:223 for head prediction -- is computed once for the four of
-    them (bit-identical results, ~15 % fewer FP32 lane-ops; 314 -> 284 us per 1,024 triples on FB15k-237).  Padding
+    its last triple.  The exact sweep kernel gives 4 consecutive triples to one warp; when they share the relation, the
+    first rounding of head prediction -- fl(candidate + r) for TransE (models.py:223), fl(candidate * r) for the
+    bilinear models (models.py:227, 235-238, 247) -- is computed once for the four of them (bit-identical results,
+    ~15 % fewer FP32 lane-ops; TransE: 314 -> 284 us per 1,024 triples on FB15k-237).  Padding
     makes that hold for EVERY warp, so one loop nest stays hot.  `rank_sweep(..., triples=AlignedTriples(t))` returns
     its outputs in the caller's original order; padding entries are computed and dropped (<= 3 per relation).
 
@@ -158,7 +159,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 (blp_rank_sweep_fast) -- scores within ~1e-6 * sum|terms|, ranks may differ for candidates
                 inside that band around the true score; `fast_table` = ops.fast_table(ent_emb) to reuse
                 the split table across calls
-    sort_by_relation   TransE exact mode, sweeps of >= 64 M scores per direction: process the triples in relation order
+    sort_by_relation   exact mode, D = 128, sweeps of >= 64 M scores per direction: process the triples in relation-aligned order (AlignedTriples)
                 (one stable argsort per sweep; the outputs come back in the caller's order).  Triples that share a relation let the kernel compute
                 fl(candidate + r) once for several head-prediction queries (~13 % fewer FP32 lane-ops); results are
                 bit-identical either way
@@ -205,7 +206,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         if mode not in ("exact", "fast"):
             raise ValueError(f"unknown mode {mode!r}")
         # worth one sort + a few small gathers only when the sweep itself is milliseconds long
-        if (aligned is None and sort_by_relation and rel_model == "transe" and mode == "exact"
+        if (aligned is None and sort_by_relation and mode == "exact"
                 and (not filtered or dev_index is not None) and ent_emb.shape[1] == 128
                 and T * ent_emb.shape[0] >= 64_000_000):
             aligned = AlignedTriples(triples)

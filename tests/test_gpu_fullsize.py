@@ -177,12 +177,13 @@ def test_umls_plumbing_config(d, cuda_device):
     assert np.abs(ent_embs.grad.cpu().numpy() - co["grad_ent"]).max() <= 2e-5 * np.abs(co["grad_ent"]).max()
 
 
+@pytest.mark.parametrize("model", ("transe", "distmult", "complex", "simple"))
 @pytest.mark.parametrize("n_rel", (3, 37, 500))
-def test_aligned_triples_sweep_is_bit_identical(n_rel, cuda_device):
+def test_aligned_triples_sweep_is_bit_identical(model, n_rel, cuda_device):
     """blp_b200.AlignedTriples: relation-sorted order with every relation's run padded to a multiple of 4, so every warp of
     the TransE kernel shares fl(candidate + r) across its head queries.  Outputs come back in the caller's order with the
     same bits as the unsorted sweep; padding entries are dropped."""
-    model, n, t = "transe", 3000, 1500
+    n, t = 3000, 1500
     ent, rel, heads, tails, rels = make_inputs(model, n, 128, t, seed=n_rel, n_rel=n_rel)
     dev = cuda_device
     e, r = ent.to(dev), rel.to(dev)

@@ -375,6 +375,250 @@ __global__ void __launch_bounds__(kTrainThreads, (NCH2 <= 2 ? BLP_TRAIN_MINB : 1
     }
 }
 
+// ---- d == 128: lane-group mapping ------------------------------------------------------------------------
+// ncu on the generic kernel above (B = 1024, K = 512): 148 warp instructions per negative, IPC 2.4 of 4, one CTA per
+// SM, 0.97 M REDG.v2 warp instructions (33 M lane-ops at ~1 lane-op / clk / SM).  With one warp per negative a lane owns
+// only 4 of the 128 dims, so the per-negative bookkeeping (index shuffles, 64-bit address arithmetic, loss weight, own /
+// foreign row decisions) is replicated 32-fold.  Here a warp is 4 groups of 8 lanes; a group scores one negative (16
+// dims per lane: four 16-byte loads per row, 3 shuffle steps per reduction), every bookkeeping instruction serves 4
+// negatives, and the gradient scatter is REDG.v4 (half the reduction lane-ops).
+#ifndef BLP_TRAIN128_UNROLL
+#define BLP_TRAIN128_UNROLL 1
+#endif
+struct V16 {
+    float v[16];
+};
+
+// lane gl of a group owns four 16-byte chunks of a 128-float row, interleaved with the other lanes so that every vector
+// load / reduction instruction of a group covers 128 contiguous bytes (whole sectors): chunks gl, gl + 8, gl + 16,
+// gl + 24 (TransE, DistMult), or chunks gl, gl + 8 of BOTH halves (ComplEx / SimplE: v[0..7] first half, v[8..15] second)
+template <int MODEL>
+__device__ __forceinline__ int v16_offset(int gl, int c) {      // float offset of the c-th 16-byte chunk
+    if (TM<MODEL>::kHalves) return (c >> 1) * 64 + 4 * (gl + 8 * (c & 1));
+    return 4 * (gl + 8 * c);
+}
+template <int MODEL>
+__device__ __forceinline__ void load_v16(V16 &x, const float *__restrict__ row, int gl) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 q = *reinterpret_cast<const float4 *>(row + v16_offset<MODEL>(gl, c));
+        x.v[4 * c] = q.x; x.v[4 * c + 1] = q.y; x.v[4 * c + 2] = q.z; x.v[4 * c + 3] = q.w;
+    }
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int MODEL>
+__device__ __forceinline__ void red_v16(float *__restrict__ row, const V16 &g, int gl, bool pred) {
+    if (!pred) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        red_add_v4(row + v16_offset<MODEL>(gl, c), g.v[4 * c], g.v[4 * c + 1], g.v[4 * c + 2], g.v[4 * c + 3]);
+}
+template <int MODEL>
+__device__ __forceinline__ float partial16(const V16 &h, const V16 &t, const V16 &r) {
+    float s = 0.f;
+    constexpr int n = TM<MODEL>::kHalves ? 8 : 16;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+        s += term1<MODEL>(h.v[i], h.v[(i + 8) & 15], t.v[i], t.v[(i + 8) & 15], r.v[i], r.v[(i + 8) & 15]);
+    return s;
+}
+__device__ __forceinline__ float group_sum(float v) {           // over the 8 lanes of a group
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+// gh / gt / gr += w * d score / d (h, t, r) on this lane's 16 floats
+template <int MODEL>
+__device__ __forceinline__ void grad16(float w, const V16 &h, const V16 &t, const V16 &r, V16 &gh, V16 &gt, V16 &gr) {
+    constexpr int n = TM<MODEL>::kHalves ? 8 : 16;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 8) & 15;
+        float a, b2, c2, d2, e, f;
+        grad1<MODEL>(w, h.v[i], h.v[j], t.v[i], t.v[j], r.v[i], r.v[j], a, b2, c2, d2, e, f);
+        gh.v[i] = a; gt.v[i] = c2; gr.v[i] = e;
+        if (TM<MODEL>::kHalves) { gh.v[j] = b2; gt.v[j] = d2; gr.v[j] = f; }
+    }
+}
+
+template <int MODEL, bool GRAD>
+__global__ void __launch_bounds__(kTrainThreads) train128_kernel(const TrainArgs a) {
+    constexpr int d = 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 3, gl = lane & 7;
+    const long long b = blockIdx.x / a.slices;
+    const int slice = blockIdx.x % a.slices;
+    const float half = (MODEL == BLP_MODEL_SIMPLE) ? 0.5f : 1.0f;
+    const long long nb2 = 2 * a.b;
+
+    long long rel = a.rels[b];
+    if (rel < 0 || rel >= a.num_rel) {
+        if (threadIdx.x == 0) *a.err_flag = 1;
+        rel = 0;
+    }
+    V16 rb;
+    load_v16<MODEL>(rb, a.rel_weight + rel * d, gl);
+    float pos;
+    {
+        V16 hb, tb;
+        load_v16<MODEL>(hb, a.ent + (2 * b) * d, gl);
+        load_v16<MODEL>(tb, a.ent + (2 * b + 1) * d, gl);
+        pos = finish_score<MODEL>(group_sum(partial16<MODEL>(hb, tb, rb)));
+    }
+    const float one_minus_pos = 1.0f - pos;
+    const float inv_bk = 1.0f / (float)(a.b * a.k);
+    V16 acc_h, acc_t, acc_r;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc_h.v[i] = acc_t.v[i] = acc_r.v[i] = 0.f;
+    float loss_part = 0.f, wsum = 0.f;           // per group (the same value in its 8 lanes)
+
+    const long long kps = (a.k + a.slices - 1) / a.slices;
+    const long long kb = slice * kps;
+    const long long ke = min(a.k, kb + kps);
+    const long long *nrow = a.neg_idx + b * a.s0;
+    const long long per_warp = (ke - kb + kTrainWarps - 1) / kTrainWarps;
+    const long long wb = kb + (long long)warp * per_warp, we = min(ke, wb + per_warp);
+    for (long long base = wb; base < we; base += 32) {
+        // the index pairs of 32 negatives with one load per lane, handed out by shuffle (4 negatives per step)
+        long long li0 = 2 * b, li1 = 2 * b + 1;
+        if (base + lane < we) {
+            li0 = nrow[(base + lane) * a.s1];
+            li1 = nrow[(base + lane) * a.s1 + a.s2];
+            if (li0 < 0 || li0 >= nb2 || li1 < 0 || li1 >= nb2) {
+                *a.err_flag = 1;
+                li0 = 2 * b; li1 = 2 * b + 1;
+            }
+        }
+        const int cnt = (int)min(32ll, we - base);
+        constexpr int kUnroll = BLP_TRAIN128_UNROLL;
+#pragma unroll kUnroll
+        for (int u0 = 0; u0 < cnt; u0 += 4) {
+            const int u = u0 + gid;
+            const bool valid = u < cnt;
+            const long long i0 = __shfl_sync(0xffffffffu, li0, u & 31), i1 = __shfl_sync(0xffffffffu, li1, u & 31);
+            V16 nh, nt;
+            load_v16<MODEL>(nh, a.ent + i0 * d, gl);
+            load_v16<MODEL>(nt, a.ent + i1 * d, gl);
+            const float sc = finish_score<MODEL>(group_sum(partial16<MODEL>(nh, nt, rb)));
+            if (a.neg_scores && valid && gl == 0) a.neg_scores[b * a.k + base + u] = sc;
+            float w;
+            if (a.loss == BLP_LOSS_MARGIN) {
+                // models.py:252-253: m = fl(fl(1 - pos) + neg); entries with m < 0 are zeroed (m == 0 keeps its gradient)
+                const float m = one_minus_pos + sc;
+                const bool keep = valid && !(m < 0.f);
+                if (keep) loss_part += m;
+                w = keep ? inv_bk : 0.f;
+                wsum += w;
+            } else {
+                // models.py:258: softplus(neg).mean() / 2
+                if (valid) loss_part += softplus_f(sc);
+                w = valid ? 0.5f * inv_bk * softplus_grad_f(sc) : 0.f;
+            }
+            if (GRAD && __any_sync(0xffffffffu, w != 0.f)) {
+                const bool own_h = (i0 == 2 * b), own_t = (i1 == 2 * b + 1);
+                V16 gh, gt, gr;
+                grad16<MODEL>(w * half, nh, nt, rb, gh, gt, gr);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    acc_r.v[i] += gr.v[i];
+                    acc_h.v[i] += own_h ? gh.v[i] : 0.f;
+                    acc_t.v[i] += own_t ? gt.v[i] : 0.f;
+                }
+                // rows sampled as corrupting entities: vector reductions into grad_ent
+                red_v16<MODEL>(a.grad_ent + i0 * d, gh, gl, !own_h && w != 0.f);
+                red_v16<MODEL>(a.grad_ent + i1 * d, gt, gl, !own_t && w != 0.f);
+            }
+        }
+    }
+
+    // positive-side gradient: margin d/dpos = -sum_k w_bk (each group adds its share); nll: -sigmoid(-pos)/(2B)
+    const bool lead = (slice == 0 && warp == 0);
+    V16 hb, tb;
+    load_v16<MODEL>(hb, a.ent + (2 * b) * d, gl);
+    load_v16<MODEL>(tb, a.ent + (2 * b + 1) * d, gl);
+    if (GRAD) {
+        const float wpos = (a.loss == BLP_LOSS_MARGIN) ? -wsum : ((lead && gid == 0) ? -0.5f * softplus_grad_f(-pos) / (float)a.b : 0.f);
+        {
+            V16 gh, gt, gr;
+            grad16<MODEL>(wpos * half, hb, tb, rb, gh, gt, gr);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc_h.v[i] += gh.v[i]; acc_t.v[i] += gt.v[i]; acc_r.v[i] += gr.v[i]; }
+        }
+        if (lead && gid == 0 && a.regularizer > 0.f) {
+            // models.py:59-62, 261-266: d/dx of regularizer * mean(x^2) / 3
+            const float cr = a.regularizer * 2.0f / (3.0f * (float)a.b * (float)d);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                acc_h.v[i] += cr * hb.v[i]; acc_t.v[i] += cr * tb.v[i]; acc_r.v[i] += cr * rb.v[i];
+            }
+        }
+        // the 4 groups of the warp hold partial rows for the same 16 floats per lane position: fold them, group 0 flushes
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            acc_h.v[i] += __shfl_xor_sync(0xffffffffu, acc_h.v[i], 8);  acc_h.v[i] += __shfl_xor_sync(0xffffffffu, acc_h.v[i], 16);
+            acc_t.v[i] += __shfl_xor_sync(0xffffffffu, acc_t.v[i], 8);  acc_t.v[i] += __shfl_xor_sync(0xffffffffu, acc_t.v[i], 16);
+            acc_r.v[i] += __shfl_xor_sync(0xffffffffu, acc_r.v[i], 8);  acc_r.v[i] += __shfl_xor_sync(0xffffffffu, acc_r.v[i], 16);
+        }
+        red_v16<MODEL>(a.grad_ent + (2 * b) * d, acc_h, gl, gid == 0);
+        red_v16<MODEL>(a.grad_ent + (2 * b + 1) * d, acc_t, gl, gid == 0);
+        red_v16<MODEL>(a.grad_rel + rel * d, acc_r, gl, gid == 0);
+    }
+
+    // ---- loss: per-CTA partial, deterministic final reduction by the last CTA
+    __shared__ float s_part[kTrainWarps];
+    __shared__ bool s_last;
+    float mine = (gl == 0) ? loss_part : 0.f;                 // one lane per group carries the group's partial
+    mine += __shfl_xor_sync(0xffffffffu, mine, 8);
+    mine += __shfl_xor_sync(0xffffffffu, mine, 16);
+    mine *= (a.loss == BLP_LOSS_MARGIN) ? inv_bk : 0.5f * inv_bk;
+    if (lead) {
+        if (a.loss == BLP_LOSS_NLL) mine += 0.5f * softplus_f(-pos) / (float)a.b;
+        if (a.regularizer > 0.f) {
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sq += hb.v[i] * hb.v[i] + tb.v[i] * tb.v[i] + rb.v[i] * rb.v[i];
+            sq = group_sum(sq);
+            mine += a.regularizer * sq / (3.0f * (float)a.b * (float)d);
+        }
+        if (lane == 0) a.pos_scores[b] = pos;
+    }
+    if (lane == 0) s_part[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w2 = 0; w2 < kTrainWarps; ++w2) tot += s_part[w2];
+        a.partials[blockIdx.x] = tot;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned int i = lane; i < gridDim.x; i += 32) tot += (double)__ldcg(a.partials + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) {
+            *a.loss_out = (float)tot;
+            *a.counter = 0u;   // leave the workspace zeroed for the next call
+        }
+    }
+}
+
+template <int MODEL>
+static int launch_train128(const TrainArgs &a, bool grad, cudaStream_t st) {
+    const unsigned grid = (unsigned)(a.b * a.slices);
+    prof_begin(2, st);
+    if (grad) train128_kernel<MODEL, true><<<grid, kTrainThreads, 0, st>>>(a);
+    else train128_kernel<MODEL, false><<<grid, kTrainThreads, 0, st>>>(a);
+    prof_end(2, st);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "train128_kernel launch");
+}
+
 template <int MODEL, int NCH2, int ILP>
 static int launch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
     const unsigned grid = (unsigned)(a.b * a.slices);
@@ -386,8 +630,18 @@ static int launch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "train_kernel launch");
 }
 
+#ifndef BLP_TRAIN128
+#define BLP_TRAIN128 1
+#endif
 template <int MODEL>
 static int dispatch_train(const TrainArgs &a, bool grad, cudaStream_t st) {
+    // d = 128 (every BLP script) with many negatives per row: lane-group kernel (rows must be 16-byte aligned for its
+    // vector loads / reductions).  Measured (TransE, margin): B = 1024, K = 512: 106 vs 121 us; B = 64, K = 512: 16.4 vs
+    // 17.0 us; with K = 64 a warp has only 4 negatives and the per-warp epilogue of this kernel costs more than it
+    // saves (B = 8192, K = 64: 338 vs 270 us), so those shapes stay on the warp-per-negative kernel
+    if (BLP_TRAIN128 && a.d == 128 && a.k >= 256 && ((reinterpret_cast<uintptr_t>(a.ent) | reinterpret_cast<uintptr_t>(a.rel_weight) |
+                                        reinterpret_cast<uintptr_t>(a.grad_ent) | reinterpret_cast<uintptr_t>(a.grad_rel)) & 15u) == 0)
+        return launch_train128<MODEL>(a, grad, st);
     const int P = TM<MODEL>::kHalves ? a.d / 2 : a.d;
     const int need = (P + 63) / 64;
 #ifndef BLP_TRAIN_ILP

@@ -60,7 +60,7 @@ def test_golden_compute_loss(name, cuda_device):
 
 @pytest.mark.parametrize("model", MODELS)
 @pytest.mark.parametrize("loss", ("margin", "nll"))
-@pytest.mark.parametrize("b,k,d", [(64, 512, 128), (2, 2, 128), (33, 70, 128), (16, 64, 256), (8, 32, 768)])
+@pytest.mark.parametrize("b,k,d", [(64, 512, 128), (5, 259, 128), (2, 2, 128), (33, 70, 128), (16, 64, 256), (8, 32, 768)])
 def test_compute_loss_vs_oracle(model, loss, b, k, d, cuda_device):
     g = torch.Generator().manual_seed(b * 1000 + k)
     ent = torch.randn(b, 2, d, generator=g)

@@ -48,17 +48,17 @@
 namespace blp {
 
 constexpr int kPitch = 132;                   // smem row pitch (floats) of the padded (bilinear) tile layout
-constexpr int kCW = 8;                        // consumer warps
+constexpr int kCW = 8;                        // consumer warps (default; Cfg<4, 2, 12> / Cfg<4, 2, 16> were measured and are slower)
 constexpr int kCT = 128;                      // candidate rows per tile
-constexpr int kThreads = (kCW + 1) * 32;
 constexpr int kSmemBudget = 227 * 1024 - 1024;
 
-template <int TQP_, int TC_>
+template <int TQP_, int TC_, int CW_ = kCW>
 struct Cfg {
     static constexpr int TQP = TQP_;          // query pairs per consumer thread
     static constexpr int TC = TC_;            // candidates per consumer thread
+    static constexpr int CW = CW_;            // consumer warps of the CTA
     static constexpr int RS = 4 / TC_;        // warps that share one slot (they split the 128 tile rows)
-    static constexpr int NS = kCW / RS;       // slots per CTA
+    static constexpr int NS = CW_ / RS;       // slots per CTA
     static constexpr int SQ = 2 * TQP_;       // queries per slot
     static constexpr int NQ = NS * SQ;        // queries per CTA
     static constexpr int QV_BYTES = NS * TQP_ * 2 * kD * 2 * 4;
@@ -82,9 +82,10 @@ struct TileLayout {
 template <int MODEL, class C>
 struct Stages {
     // per query: 128 term floats (in-kernel true scores) + three row pointers + flags
-    static constexpr int kPerWarp = (C::NQ + kCW - 1) / kCW;                // queries per warp (ql = warp + kCW * u)
-    static constexpr int kRound = kPerWarp < 4 ? kPerWarp : 4;               // queries per warp and round
-    static constexpr int kTermRows = kCW * kRound;
+    static constexpr int kPerWarp = (C::NQ + C::CW - 1) / C::CW;            // queries per warp (ql = warp + CW * u)
+    static constexpr int kRoundMax = C::CW > 8 ? 2 : 4;                     // (16 warps: 2, the term rows must fit next to the tiles)
+    static constexpr int kRound = kPerWarp < kRoundMax ? kPerWarp : kRoundMax;   // queries per warp and round
+    static constexpr int kTermRows = C::CW * kRound;
     static constexpr int kPrologueBytes = kTermRows * kD * 4 + C::NQ * (3 * 8 + 3 * 4 + 4);
     static constexpr int ST = (C::QV_BYTES + kPrologueBytes + 3 * TileLayout<MODEL>::kFloats * 4 <= kSmemBudget) ? 3 : 2;   // tile buffers
 };
@@ -529,9 +530,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
         if (args.dbg && tid == 0) args.dbg[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();      \
     } while (0)
 
-__device__ __forceinline__ void consumer_bar_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory");
+template <int CW>
+__device__ __forceinline__ void consumer_bar_sync_n() {
+    asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
 }
+#define consumer_bar_sync() consumer_bar_sync_n<C::CW>()
 
 // How the queries of a triple group map onto slots (a slot = the SQ queries of one warp-set):
 //   ROLES == 3, TQP >= 2  "mixed": every slot takes TQP triples; its first TQP queries (pairs [0, TQP/2))
@@ -560,7 +563,7 @@ struct QueryMap {
 };
 
 template <int MODEL, class C, int ROLES>
-__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepArgs args, const __grid_constant__ CUtensorMap tmap) {
     using QM = QueryMap<C, ROLES>;
     using SM = SweepSmem<MODEL, C>;
     extern __shared__ unsigned char smem_raw[];
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
     if (tid == 0) {
         for (int s = 0; s < SM::ST; ++s) {
             mbar_init(&sm.full_bar[s], 1);
-            mbar_init(&sm.empty_bar[s], kCW);
+            mbar_init(&sm.empty_bar[s], C::CW);
         }
         mbar_fence_init();
     }
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
     const long long total = ntiles * args.groups;
     const long long id_begin = total * blockIdx.x / gridDim.x, id_end = total * (blockIdx.x + 1) / gridDim.x;
 
-    if (warp == kCW) {
+    if (warp == C::CW) {
         // ===================== producer warp =====================
         int it = 0;
         for (long long id = id_begin; id < id_end; ++id, ++it) {
@@ -671,15 +674,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         // the 128 dependent adds of torch.norm(p=1) for the round's u-th query; for torch.sum, lanes 8u .. 8u+7 run
         // ATen's 8-lane x 4-accumulator cascade of the u-th query.
         constexpr bool kHalves = MODEL == BLP_MODEL_COMPLEX || MODEL == BLP_MODEL_SIMPLE;
-        constexpr int kPerWarp = (C::NQ + kCW - 1) / kCW;              // this warp's queries: ql = warp + kCW * u
+        constexpr int kPerWarp = (C::NQ + C::CW - 1) / C::CW;          // this warp's queries: ql = warp + CW * u
         constexpr int kTermRows = Stages<MODEL, C>::kTermRows;
         constexpr int L = kHalves ? kD / 2 : kD;
         const int tm0 = warp * Stages<MODEL, C>::kRound;                // this warp's term rows
+        constexpr int kR = Stages<MODEL, C>::kRound;                    // queries per warp and round (<= 4)
 #pragma unroll 1
-        for (int u0 = 0; u0 < kPerWarp; u0 += 4) {
+        for (int u0 = 0; u0 < kPerWarp; u0 += kR) {
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-                const int ql = warp + kCW * (u0 + uu);
+            for (int uu = 0; uu < kR; ++uu) {
+                const int ql = warp + C::CW * (u0 + uu);
                 if (u0 + uu >= kPerWarp || ql >= C::NQ) continue;     // warp-uniform
                 const int s_ = ql / C::SQ, qi = ql % C::SQ;
                 const bool hp = QM::is_head(s_, qi);
@@ -726,8 +730,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
             float sv = 0.0f;
             int uu_mine = -1;                                          // the chain this lane finishes
             if (MODEL == BLP_MODEL_TRANSE) {
-                if (lane < 4) {
-                    const float *tu = &sm.tm[tm0 + (lane < Stages<MODEL, C>::kRound ? lane : 0)][0];
+                if (lane < kR) {
+                    const float *tu = &sm.tm[tm0 + lane][0];
 #pragma unroll 8
                     for (int j = 0; j < kD; j += 4) {
                         const float4 v = *reinterpret_cast<const float4 *>(tu + j);
@@ -748,10 +752,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #pragma unroll
                 for (int ll = 0; ll < 8; ++ll) sv = fadd(sv, __shfl_sync(0xffffffffu, cl, (lane & 24) + ll));
                 if (MODEL == BLP_MODEL_SIMPLE) sv = fmul(sv, 0.5f);
-                if (l == 0) uu_mine = uu;
+                if (l == 0 && uu < kR) uu_mine = uu;
             }
             if (uu_mine >= 0) {
-                const int ql = warp + kCW * (u0 + uu_mine);
+                const int ql = warp + C::CW * (u0 + uu_mine);
                 if (u0 + uu_mine < kPerWarp && ql < C::NQ) {
                     const int s_ = ql / C::SQ, qi = ql % C::SQ;
                     const long long tr = t0 + QM::triple(s_, qi);
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #define BLP_SHARED_R 1
 #endif
         bool shared_r = false;
-        if (BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && C::TC == 4) {   // only the full register tile gains
+        if (BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && (C::TC == 4 || C::CW > 8)) {   // only the 32-triple groups gain
             shared_r = true;
 #pragma unroll
             for (int s_ = 0; s_ < C::NS; ++s_) {
@@ -826,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
 #ifndef BLP_FORCE_SHARED
 #define BLP_FORCE_SHARED 0      // timing experiment only: the shared-relation loop nest alone (wrong results unless every slot shares r)
 #endif
-                constexpr bool kCanShare = BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && C::TC == 4;
+                constexpr bool kCanShare = BLP_SHARED_R && QM::kMixed && C::TQP >= 2 && (C::TC == 4 || C::CW > 8);
                 if (kCanShare && (BLP_FORCE_SHARED || shared_r))
                     score_tile<MODEL, kRoleMixed, C::TQP, C::TC, true>(tv, qv, args.negzero2, sp);
                 else if (QM::kMixed && !(kCanShare && BLP_FORCE_SHARED)) score_tile<MODEL, kRoleMixed, C::TQP, C::TC>(tv, qv, args.negzero2, sp);
@@ -905,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
     double acc[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) acc[j] = 0.0;
-    for (long long i = tid; i < args.out_len; i += kCW * 32) {
+    for (long long i = tid; i < args.out_len; i += C::CW * 32) {
         const bool live = i < args.b || i >= args.tail_off;       // [b, tail_off) is a gap when the outputs are slices
         if (!live) continue;
         const int g = __ldcg(args.gt + i), e = __ldcg(args.ge + i);
@@ -935,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepArgs args
         consumer_bar_sync();
         if (tid <= args.kv.nk) {
             double tot = 0.0;
-            for (int w = 0; w < kCW; ++w) tot += s_red[w][tid];
+            for (int w = 0; w < C::CW; ++w) tot += s_red[w][tid];
             args.sums[tid] = tot;
         }
     }
@@ -1034,7 +1038,7 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     }
     if (!(MODEL == BLP_MODEL_TRANSE && args.use_tma)) memset(&tmap, 0, sizeof(tmap));
     prof_begin(1, st);
-    sweep_kernel<MODEL, C, ROLES><<<grid, kThreads, smem, st>>>(args, tmap);
+    sweep_kernel<MODEL, C, ROLES><<<grid, (C::CW + 1) * 32, smem, st>>>(args, tmap);
     prof_end(1, st);
     count_launch();
     BLP_CUDA(cudaGetLastError());

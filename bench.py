@@ -411,7 +411,7 @@ def sweep_roofline(model, mode, n, d, q_per_launch, kern_s, peaks, fp32_peak, hb
     alg_bytes = n * d * 4 + (q_per_launch // 2) * 3 * d * 4 + q_per_launch * 12
     out = {"kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
            "hbm_GBps_algorithmic": alg_bytes / kern_s / 1e9, "hbm_frac": alg_bytes / kern_s / 1e9 / hbm_peak}
-    if mode == "fast":
+    if mode.startswith("fast"):
         flops = 2.0 * q_per_launch * n * d
         f16_peak = float(peaks.get("bf16_tflops", 2250.0))
         out.update({"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
@@ -574,7 +574,7 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
                 return out
         else:
             chunks = [tr[torch.arange(c * e, (c + 1) * e) % w["t"]].contiguous().to(dev) for c in range(max(1, w["t"] // e))]
-            ft = ops.fast_table(ent) if mode == "fast" else None
+            ft = ops.fast_table(ent) if mode.startswith("fast") else None
             plan = blp_b200.RankSweepPlan(model, ent, rel, e, mode=mode, fast_table=ft)
 
             def call():
@@ -591,6 +591,13 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
                "sweep_s_all_test_triples": ms * 1e-3 * w["t"] / e, "mrr": float(out["sums"][0]) / (2 * e)}
         leg["roofline"] = sweep_roofline(model, mode, w["n"], w["d"], 2 * e, ms * 1e-3, peaks, fp32_peak, hbm_peak,
                                          {"timed": "whole call (all launches of the call), back to back"}, exec_ops=exec_ops)
+        leg["_sums"] = out["sums"].detach().cpu()
+        if mode == "fast_exact":
+            st = out["refine_state"].cpu()
+            leg["refine_band_candidates_per_query"] = int(st[0]) / (2 * e)
+            leg["refine_overflow"] = bool(int(st[1]))
+            leg["note"] = ("tensor-core sweep + exact re-scoring of the candidates inside the a-priori error band around the true "
+                           "score: integer ranks bit-identical to the exact mode (DESIGN 4.2b)")
         legs[name] = leg
 
     # one call per evaluation set, like the headline step (FB15k-237: 20,480 test triples, WN18RR: 3,136)
@@ -598,6 +605,16 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
     sweep_leg("fb15k237_distmult_fast", "fb15k237", "distmult", "fast", 20480)
     sweep_leg("wn18rr_complex_exact", "wn18rr", "complex", "exact", 3136)
     sweep_leg("wn18rr_complex_fast", "wn18rr", "complex", "fast", 3136)
+    sweep_leg("fb15k237_distmult_fast_exact", "fb15k237", "distmult", "fast_exact", 20480)
+    sweep_leg("wn18rr_complex_fast_exact", "wn18rr", "complex", "fast_exact", 3136)
+    for ds_model in ("fb15k237_distmult", "wn18rr_complex"):
+        # the exact leg ranks the same triples (relation-aligned order only permutes them): identical fp64 metric sums
+        # up to the order of the final fp64 additions, so compare the hit COUNTS exactly and the MRR sum to 1e-12
+        a_, b_ = legs[ds_model + "_exact"]["_sums"], legs[ds_model + "_fast_exact"]["_sums"]
+        legs[ds_model + "_fast_exact"]["metrics_equal_exact_leg"] = bool(
+            torch.equal(a_[1:], b_[1:]) and abs(float(a_[0]) - float(b_[0])) <= 1e-12 * abs(float(a_[0])))
+    for leg in legs.values():
+        leg.pop("_sums", None)
     sweep_leg("fb15k237_transe_eval_batch_64", "fb15k237", "transe", "exact", 64)     # the reference's eval_batch_size
 
     # BOW script widths (TransE, D = 300 glove-bow / 768 bert-bow, scripts/test-umls.sh): the D != 128 path
@@ -951,6 +968,7 @@ def main_b200(args):
                          "sharded_parity": wd["parity"]["sharded_parity"]})
     if legs and "error" not in legs:
         for nm, tag in (("fb15k237_distmult_fast", "distmult_fast"), ("fb15k237_distmult_exact", "distmult_exact"),
+                        ("fb15k237_distmult_fast_exact", "distmult_fast_exact"), ("wn18rr_complex_fast_exact", "complex_fast_exact"),
                         ("wn18rr_complex_fast", "complex_fast"), ("wn18rr_complex_exact", "complex_exact"),
                         ("fb15k237_transe_eval_batch_64", "transe_e64"), ("fb15k237_transe_d768", "transe_d768"),
                         ("train_transe_b1024_k512", "train_b1024")):

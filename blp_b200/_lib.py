@@ -45,6 +45,9 @@ SYMBOLS = {
     "blp_fast_prepare_table": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "blp_rank_sweep_fast": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "blp_fast_refine_bytes": (_i64, [_i64]),
+    "blp_rank_sweep_fast_exact": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "blp_rank_metrics": (_i32, [_vp, _vp, _i64, ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp]),
     "blp_train_workspace_bytes": (_i64, [_i64, _i64]),
     "blp_train_loss": (_i32, [_i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _f32,

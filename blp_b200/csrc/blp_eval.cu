@@ -266,6 +266,7 @@ struct RankJob {
     int force_cfg;                                 // -1 auto
     // tensor-core mode
     const long long *triples; const void *fast_table_ws; void *fast_query_ws; float *fast_scores; long long fast_ld;
+    void *fast_refine_ws; long long fast_refine_cap;   // filter + refine: exact ranks on the tensor path (NULL = plain fast mode)
     int phases;                                    // bit 0: true scores + counter reset, bit 1: sweep (+ CSR filter correction)
 };
 
@@ -326,7 +327,8 @@ static int rank_impl(const RankJob &j, cudaStream_t st) {
     if (n_local > 0 && j.fast_table_ws) {
         // tensor-core mode: scores as a split-FP16 contraction on tcgen05, same counters (blp_fast.cu)
         const int rc = launch_fast_sweep(model, n_local, j.ent_offset, j.h, j.t, j.r, j.triples, b, tail_off, j.true_score,
-                                         j.gt, j.ge, j.fast_table_ws, j.fast_query_ws, j.fast_scores, j.fast_ld, fused_true, st);
+                                         j.gt, j.ge, j.fast_table_ws, j.fast_query_ws, j.fast_scores, j.fast_ld, fused_true, j.ent,
+                                         j.fast_refine_ws, j.fast_refine_cap, st);
         if (rc) return rc;
     } else if (n_local > 0) {
         if (d == kD && aligned16(j.ent)) {
@@ -659,12 +661,50 @@ extern "C" int blp_fast_prepare_table(const float *ent, int64_t n_local, int d, 
     return fast_prepare_table(ent, n_local, table_ws, (cudaStream_t)stream);
 }
 
+extern "C" int64_t blp_fast_refine_bytes(int64_t capacity) { return fast_refine_ws_bytes(capacity); }
+
+static int rank_sweep_fast_impl(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                                const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                                const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                                int32_t *ge_f, float *true_score, const void *table_ws, void *query_ws,
+                                float *scores_out, int64_t ld_scores, void *refine_ws, int64_t refine_capacity, void *stream);
+
 extern "C" int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
                                    const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
                                    const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
                                    const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
                                    int32_t *ge_f, float *true_score, const void *table_ws, void *query_ws,
                                    float *scores_out, int64_t ld_scores, void *stream) {
+    return rank_sweep_fast_impl(model, ent, n_local, ent_offset, d, rel_weight, num_rel, triples, t, h_rows, t_rows, filt_indptr,
+                                filt_idx, tail_off, gt, ge, gt_f, ge_f, true_score, table_ws, query_ws, scores_out, ld_scores,
+                                nullptr, 0, stream);
+}
+
+extern "C" int blp_rank_sweep_fast_exact(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                         const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                                         const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                                         const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                                         int32_t *ge_f, float *true_score, const void *table_ws, void *query_ws,
+                                         void *refine_ws, int64_t refine_capacity, void *stream) {
+    if (!refine_ws || refine_capacity <= 0) { set_error("blp_rank_sweep_fast_exact needs a refine workspace"); return BLP_EINVAL; }
+    if (refine_capacity >= (1ll << 31)) { set_error("refine_capacity must be < 2^31"); return BLP_EINVAL; }
+    if (n_local >= (1ll << 31) || 2 * t >= (1ll << 31)) { set_error("refine entries are int32 (query, candidate) pairs"); return BLP_EINVAL; }
+    if (!aligned16(ent) || !aligned16(rel_weight) || !aligned16(h_rows) || !aligned16(t_rows) || !aligned16(refine_ws)) {
+        set_error("ent / rel_weight / h_rows / t_rows / refine_ws must be 16-byte aligned");
+        return BLP_EINVAL;
+    }
+    return rank_sweep_fast_impl(model, ent, n_local, ent_offset, d, rel_weight, num_rel, triples, t, h_rows, t_rows, filt_indptr,
+                                filt_idx, tail_off, gt, ge, gt_f, ge_f, true_score, table_ws, query_ws, nullptr, 0, refine_ws,
+                                refine_capacity, stream);
+}
+
+static int rank_sweep_fast_impl(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                                const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                                const float *h_rows, const float *t_rows, const int64_t *filt_indptr,
+                                const int64_t *filt_idx, int64_t tail_off, int32_t *gt, int32_t *ge, int32_t *gt_f,
+                                int32_t *ge_f, float *true_score, const void *table_ws, void *query_ws,
+                                float *scores_out, int64_t ld_scores, void *refine_ws, int64_t refine_capacity, void *stream) {
     reset_launch_count();
     int rc = check_rank_args(model, d, t, n_local, ent, filt_indptr, filt_idx, gt, ge, gt_f, ge_f, true_score);
     if (rc) return rc;
@@ -680,6 +720,7 @@ extern "C" int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local,
     j.filt_indptr = (const long long *)filt_indptr; j.filt_idx = (const long long *)filt_idx; j.gt_f = gt_f; j.ge_f = ge_f;
     j.triples = (const long long *)triples; j.fast_table_ws = table_ws; j.fast_query_ws = query_ws; j.fast_scores = scores_out;
     j.fast_ld = ld_scores;
+    j.fast_refine_ws = refine_ws; j.fast_refine_cap = refine_capacity;
     return rank_impl(j, (cudaStream_t)stream);
 }
 

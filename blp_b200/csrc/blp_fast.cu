@@ -63,6 +63,14 @@ struct __align__(1024) FastSmem {
     uint32_t tmem_base;
 };
 
+// Worklist of the refine pass: (query row q in [0, 2b), local candidate row) pairs.
+struct RefineList {
+    unsigned int count;                    // appended entries (may exceed the capacity: the excess is dropped and flagged)
+    unsigned int overflow;                 // sticky: set by the refine kernel when count > capacity
+    unsigned int pad[2];
+    int2 entries[1];
+};
+
 struct FastArgs {
     long long n_local, ent_offset, n_pad;  // candidates in this shard, global id of row 0, rows per half of the split table
     long long b, tail_off, q_pad;          // triples, output slot offset of tail queries, rows per half of the split queries
@@ -74,7 +82,13 @@ struct FastArgs {
     float *scores_out;                     // optional (2b, ld_scores) matrix of the fast scores (verification aid)
     long long ld_scores;
     int debug;                             // timing experiments (BLP_FAST_DEBUG): 1 = no epilogue work, 2 = no B loads, 4 = no MMAs
+    // ---- exact ranks on the tensor path (filter + refine): candidates whose fast score lies within `band[q]` of the
+    // scaled true score are not counted here but appended to the worklist and re-scored in the reference's fp32 order
+    const float *band;                     // [q_pad] a-priori bound on |fast - reference| in the scaled domain (NULL = plain fast mode)
+    RefineList *refine;                    // worklist (header + entries)
+    long long refine_cap;
 };
+
 
 // ---- PTX wrappers (tcgen05) ---------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -161,7 +175,25 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int idx) {
 struct FastTableHeader {
     float scale;
     unsigned int max_bits;
+    unsigned int max_norm_bits;            // max over rows of ||e||_2 (fp32, rounded up a little): the refine band uses it
 };
+
+// max_e ||e||_2 over the table rows, one warp per row
+__global__ void table_maxnorm_kernel(const float4 *__restrict__ ent, long long n_local, unsigned int *__restrict__ max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    float m = 0.0f;
+    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_local;
+         row += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const float4 v = __ldg(ent + row * (kD / 4) + lane);
+        float q = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        m = fmaxf(m, q);
+    }
+    // sqrt and the fp32 summation above carry a few ulps of error: 1 + 2^-16 covers them with a wide margin
+    m = sqrtf(m) * 1.0000153f;
+    if (lane == 0 && m > 0.0f && m < 3.0e38f) atomicMax(max_norm_bits, __float_as_uint(m));
+}
 
 __global__ void table_maxabs_kernel(const float4 *__restrict__ ent, long long total4, unsigned int *__restrict__ max_bits) {
     float m = 0.0f;
@@ -221,6 +253,22 @@ __device__ __forceinline__ float fold_coeff(bool head_pred, const float *__restr
     return first ? fmul(0.5f, fmul(r[L + k], h[L + k])) : fmul(0.5f, fmul(h[k], r[k]));
 }
 
+// sum_j fold_abs(j) * |e[j]| bounds the sum of |terms| the reference adds up for candidate e: the magnitude the
+// a-priori error bound of the refine band is relative to (ComplEx folds two products into one coefficient, which may
+// cancel; everything else is a single product, so the bound is |coefficient|).
+template <int MODEL>
+__device__ __forceinline__ float fold_abs(bool head_pred, const float *__restrict__ h, const float *__restrict__ t,
+                                          const float *__restrict__ r, int j, float c) {
+    if (MODEL != BLP_MODEL_COMPLEX) return fabsf(c);
+    constexpr int L = kD / 2;
+    const int k = j & (L - 1);
+    const bool first = j < L;
+    const float rr = fabsf(r[k]), ri = fabsf(r[L + k]);
+    const float *x = head_pred ? t : h;
+    const float xr = fabsf(x[k]), xi = fabsf(x[L + k]);
+    return first ? rr * xr + ri * xi : rr * xi + ri * xr;
+}
+
 // One CTA of 128 threads per query row: rows [0, b) predict heads, [b, 2b) predict tails, the rest is padding.
 // With `true_score` given, the block of head query i also produces the exact true-triple score of triple i (warp 0,
 // true_score_warp128) and resets the counters of both of its queries, which saves the separate true-score launch.
@@ -231,18 +279,21 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
                                                           long long *__restrict__ self_id, float *__restrict__ qscale,
                                                           const FastTableHeader *__restrict__ table_hdr,
                                                           long long tail_off, float *__restrict__ true_score,
-                                                          int *__restrict__ gt, int *__restrict__ ge) {
+                                                          int *__restrict__ gt, int *__restrict__ ge,
+                                                          float *__restrict__ band, float kappa) {
     __shared__ float s_max[kD / 32];
+    __shared__ float s_sq[kD / 32];
     __shared__ __align__(16) float s_terms[kD];
     const long long q = blockIdx.x;
     const int j = threadIdx.x;
-    float c = 0.0f;
+    float c = 0.0f, ca = 0.0f;
     long long self = -1;
     if (q < 2 * b) {
         const bool head_pred = q < b;
         const long long i = head_pred ? q : q - b;
         const float *h = hr.row(i, kD), *t = tr.row(i, kD), *r = rr.row(i, kD);
         c = fold_coeff<MODEL>(head_pred, h, t, r, j);
+        ca = fold_abs<MODEL>(head_pred, h, t, r, j, c);
         self = triples[i * 3 + (head_pred ? 0 : 1)];
         if (true_score && head_pred && j < 32) {
             float s = true_score_warp128<MODEL>(h, t, r, s_terms, j);
@@ -256,10 +307,13 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
         }
     }
     // per-row power-of-two scale from the row's max |c|
-    float m = fabsf(c);
+    float m = fabsf(c), n2 = ca * ca;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((j & 31) == 0) s_max[j >> 5] = m;
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    if ((j & 31) == 0) { s_max[j >> 5] = m; s_sq[j >> 5] = n2; }
     __syncthreads();
     m = fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3]));
     const float sq = pow2_scale(m);
@@ -270,6 +324,10 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
     if (j == 0) {
         self_id[q] = self;
         qscale[q] = fmul(sq, table_hdr->scale);
+        // refine band, scaled like the accumulator: kappa * ||fold_abs||_2 * max_e ||e||_2 >= kappa * sum|terms| for every
+        // candidate (Cauchy-Schwarz); 1.001 covers the fp32 roundings of the norm itself
+        const float cn = sqrtf((s_sq[0] + s_sq[1]) + (s_sq[2] + s_sq[3])) * 1.001f;
+        band[q] = kappa * (cn * sq) * (__uint_as_float(table_hdr->max_norm_bits) * table_hdr->scale);
     }
 }
 
@@ -387,12 +445,12 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
         const int ew = warp & 3, part = (warp - 4) >> 2, row = ew * 32 + lane;
         long long cur_m = -1;
         long long slot[kFH], self_local[kFH];
-        float th[kFH], inv[kFH];                                         // scaled true score, 1 / scale
+        float th[kFH], inv[kFH], bd[kFH];                                // scaled true score, 1 / scale, refine band
         bool valid_q[kFH];
         int cgt[kFH], cge[kFH];
         int halves = kFH;
 #pragma unroll
-        for (int h = 0; h < kFH; ++h) { slot[h] = -1; self_local[h] = -1; th[h] = 0.f; inv[h] = 1.f; valid_q[h] = false; cgt[h] = cge[h] = 0; }
+        for (int h = 0; h < kFH; ++h) { slot[h] = -1; self_local[h] = -1; th[h] = 0.f; inv[h] = 1.f; bd[h] = 0.f; valid_q[h] = false; cgt[h] = cge[h] = 0; }
         uint32_t it = 0;
         auto flush = [&]() {
 #pragma unroll
@@ -419,6 +477,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                         const float qs = args.qscale[q];
                         th[h] = fmul(st, qs);                            // power-of-two scale: exact
                         inv[h] = __frcp_rn(qs);
+                        bd[h] = args.band ? args.band[q] : 0.f;
                         self_local[h] = args.self_id[q] - args.ent_offset;
                         valid_q[h] = st == st;                           // NaN = flagged triple (bad index)
                     }
@@ -450,25 +509,42 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                             if (ch * 32 + c < nvalid) orow[c] = fmul(__uint_as_float(v[c]), inv[h]);
                     }
                     if (valid_q[h]) {
+                        // plain fast mode: bd == 0, both thresholds are the scaled true score.  Refine mode: `g` counts the
+                        // candidates that beat the true score for certain (s > st + band), `e` those that may tie or beat
+                        // it (s >= st - band); the difference is the band, which goes to the worklist
+                        const float st_hi = st + bd[h], st_lo = st - bd[h];
                         int g[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};    // independent chains
                         if (nvalid == kFN) {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float s = __uint_as_float(v[c]);
-                                g[c & 3] += s > st;
-                                e[c & 3] += s >= st;
+                                g[c & 3] += s > st_hi;
+                                e[c & 3] += s >= st_lo;
                             }
                         } else {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float s = __uint_as_float(v[c]);
                                 const bool ok = ch * 32 + c < nvalid;
-                                g[c & 3] += ok && s > st;
-                                e[c & 3] += ok && s >= st;
+                                g[c & 3] += ok && s > st_hi;
+                                e[c & 3] += ok && s >= st_lo;
                             }
                         }
                         int gs = (g[0] + g[1]) + (g[2] + g[3]), es = (e[0] + e[1]) + (e[2] + e[3]);
-                        if (self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
+                        if (args.refine) {
+                            if (es != gs) {                              // rare: a few candidates per query and sweep
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) {
+                                    const float s = __uint_as_float(v[c]);
+                                    if (ch * 32 + c < nvalid && s >= st_lo && !(s > st_hi)) {
+                                        const unsigned int at = atomicAdd(&args.refine->count, 1u);
+                                        if ((long long)at < args.refine_cap)
+                                            args.refine->entries[at] = make_int2((int)q, (int)(tile_base + ch * 32 + c));
+                                    }
+                                }
+                            }
+                            es = gs;                                     // the refine kernel adds the band's exact verdicts
+                        } else if (self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
                             // the true entity itself: it ties with s_true by definition (utils.py:104-105), whatever
                             // the fast arithmetic produced for it
                             const float s_self = __uint_as_float(select32(v, (int)(self_col & 31)));
@@ -490,6 +566,57 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- refine pass: exact verdicts for the band -----------------------------------------------------------
+// Every worklist entry (query q, candidate row) is re-scored with the reference's own fp32 operations and summation
+// order (true_scores_warp128x4: the same code that produces the true-triple scores, so the true entity ties itself
+// bit for bit) and compared with the exact true score; four entries per warp, their summation chains side by side.
+// With the certain counts of the sweep kernel this makes gt / ge equal to the exact mode's, as long as the band
+// really bounds |fast - reference| (tests/test_gpu_fast.py compares the two modes bit for bit).
+constexpr int kRefineWarps = 8;
+template <int MODEL>
+__global__ void __launch_bounds__(kRefineWarps * 32) refine_kernel(RefineList *__restrict__ wl, long long cap,
+                                                                   const float *__restrict__ ent, const RowRef hr,
+                                                                   const RowRef tr, const RowRef rr, long long b,
+                                                                   long long tail_off, const float *__restrict__ true_score,
+                                                                   int *__restrict__ gt, int *__restrict__ ge) {
+    __shared__ __align__(16) float tm[kRefineWarps][4 * kD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int count = *reinterpret_cast<volatile unsigned int *>(&wl->count);
+    const long long n = (long long)count < cap ? (long long)count : cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (long long)count > cap) wl->overflow = 1u;   // entries were dropped: results invalid
+    const long long stride = (long long)gridDim.x * kRefineWarps * 4;
+    for (long long base = ((long long)blockIdx.x * kRefineWarps + warp) * 4; base < n; base += stride) {
+        const int nj = (int)(n - base < 4 ? n - base : 4);
+        const float *h[4], *t[4], *r[4];
+        long long slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            h[u] = t[u] = r[u] = ent;
+            slot[u] = -1;
+            if (u < nj) {
+                const int2 e = wl->entries[base + u];
+                const long long q = e.x;
+                const bool head_pred = q < b;
+                const long long i = head_pred ? q : q - b;
+                const float *c = ent + (long long)e.y * kD;
+                slot[u] = head_pred ? i : tail_off + i;
+                h[u] = head_pred ? c : hr.row(i, kD);
+                t[u] = head_pred ? tr.row(i, kD) : c;
+                r[u] = rr.row(i, kD);
+            }
+        }
+        const float s = true_scores_warp128x4<MODEL>(h, t, r, nj, tm[warp], lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < nj && lane == true_job_lane<MODEL>(u)) {
+                const float st = true_score[slot[u]];
+                if (s > st) atomicAdd(gt + slot[u], 1);
+                if (s >= st) atomicAdd(ge + slot[u], 1);
+            }
+        }
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -527,8 +654,10 @@ long long fast_table_ws_bytes(long long n_local) { return 2 * round_up(n_local >
 // queries: hi + lo halves of q_pad rows, self ids, scales
 long long fast_query_ws_bytes(long long t) {
     const long long q_pad = round_up(2 * (t > 0 ? t : 1), kFH * kFM);
-    return 2 * q_pad * kD * 2 + q_pad * 8 + q_pad * 4;
+    return 2 * q_pad * kD * 2 + q_pad * 8 + q_pad * 4 + q_pad * 4;     // + the refine band per query row
 }
+// worklist of the refine pass: header + capacity (query, candidate) pairs
+long long fast_refine_ws_bytes(long long capacity) { return 16 + 8 * (capacity > 0 ? capacity : 1); }
 
 int fast_prepare_table(const float *ent, long long n_local, void *table_ws, cudaStream_t st) {
     const long long n_pad = round_up(n_local > 0 ? n_local : 1, kFN);
@@ -540,6 +669,13 @@ int fast_prepare_table(const float *ent, long long n_local, void *table_ws, cuda
         long long blocks = (total4 + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         table_maxabs_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(ent), total4, &hdr->max_bits);
+        count_launch();
+        BLP_CUDA(cudaGetLastError());
+    }
+    if (n_local > 0) {
+        long long blocks = (n_local * 32 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        table_maxnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(ent), n_local, &hdr->max_norm_bits);
         count_launch();
         BLP_CUDA(cudaGetLastError());
     }
@@ -563,7 +699,7 @@ static int num_sms_fast() {
 int launch_fast_sweep(int model, long long n_local, long long ent_offset, const RowRef &h, const RowRef &t, const RowRef &r,
                       const long long *triples, long long b, long long tail_off, float *true_score, int *gt, int *ge,
                       const void *table_ws, void *query_ws, float *scores_out, long long ld_scores, bool compute_true,
-                      cudaStream_t st) {
+                      const float *ent, void *refine_ws, long long refine_cap, cudaStream_t st) {
     if (model != BLP_MODEL_DISTMULT && model != BLP_MODEL_COMPLEX && model != BLP_MODEL_SIMPLE) {
         set_error("fast (tensor-core) mode covers distmult / complex / simple; transe is an L1 distance, not a contraction");
         return BLP_EINVAL;
@@ -575,6 +711,19 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     __half *qsplit = reinterpret_cast<__half *>(query_ws);
     long long *self_id = reinterpret_cast<long long *>(qsplit + 2 * a.q_pad * kD);
     float *qscale = reinterpret_cast<float *>(self_id + a.q_pad);
+    float *band = qscale + a.q_pad;
+    // refine band: kappa bounds |fast - reference| relative to ||fold_abs||_2 * max ||e||_2
+    static const float kappa = []() {
+        const char *e = getenv("BLP_FAST_KAPPA");          // experiments only
+        const float v = e ? (float)atof(e) : 0.0f;
+        return v > 0.0f ? v : 2.0e-5f;
+    }();
+    if (refine_ws) {
+        a.band = band;
+        a.refine = reinterpret_cast<RefineList *>(refine_ws);
+        a.refine_cap = refine_cap;
+        BLP_CUDA(cudaMemsetAsync(&a.refine->count, 0, sizeof(unsigned int), st));
+    }
     const __half *table = reinterpret_cast<const __half *>(table_ws);
     const FastTableHeader *hdr = reinterpret_cast<const FastTableHeader *>(table + 2 * a.n_pad * kD);
     a.true_score = true_score; a.self_id = self_id; a.qscale = qscale; a.gt = gt; a.ge = ge;
@@ -586,9 +735,9 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
 
     float *ts_out = compute_true ? true_score : nullptr;
     switch (model) {
-    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
-    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
-    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge); break;
+    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
+    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
+    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
     }
     count_launch();
     BLP_CUDA(cudaGetLastError());
@@ -611,6 +760,16 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     prof_end(1, st);
     count_launch();
     BLP_CUDA(cudaGetLastError());
+    if (refine_ws) {
+        const unsigned rgrid = (unsigned)(sms * 4);
+        switch (model) {
+        case BLP_MODEL_DISTMULT: refine_kernel<BLP_MODEL_DISTMULT><<<rgrid, kRefineWarps * 32, 0, st>>>(a.refine, refine_cap, ent, h, t, r, b, tail_off, true_score, gt, ge); break;
+        case BLP_MODEL_COMPLEX: refine_kernel<BLP_MODEL_COMPLEX><<<rgrid, kRefineWarps * 32, 0, st>>>(a.refine, refine_cap, ent, h, t, r, b, tail_off, true_score, gt, ge); break;
+        default: refine_kernel<BLP_MODEL_SIMPLE><<<rgrid, kRefineWarps * 32, 0, st>>>(a.refine, refine_cap, ent, h, t, r, b, tail_off, true_score, gt, ge); break;
+        }
+        count_launch();
+        BLP_CUDA(cudaGetLastError());
+    }
     return BLP_OK;
 }
 

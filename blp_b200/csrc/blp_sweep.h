@@ -223,11 +223,12 @@ int launch_sweep_wide(const SweepArgs &a, int d, cudaStream_t st);
 // tensor-core fast mode (blp_fast.cu)
 long long fast_table_ws_bytes(long long n_local);
 long long fast_query_ws_bytes(long long t);
+long long fast_refine_ws_bytes(long long capacity);
 int fast_prepare_table(const float *ent, long long n_local, void *table_ws, cudaStream_t st);
 int launch_fast_sweep(int model, long long n_local, long long ent_offset, const RowRef &h, const RowRef &t, const RowRef &r,
                       const long long *triples, long long b, long long tail_off, float *true_score, int *gt, int *ge,
                       const void *table_ws, void *query_ws, float *scores_out, long long ld_scores, bool compute_true,
-                      cudaStream_t st);
+                      const float *ent, void *refine_ws, long long refine_cap, cudaStream_t st);
 int sweep_env_use_tma();
 unsigned long long *debug_timestamp_buffer();
 int sweep_cfg_for_group(long long group_triples);

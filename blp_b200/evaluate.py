@@ -159,6 +159,12 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 (blp_rank_sweep_fast) -- scores within ~1e-6 * sum|terms|, ranks may differ for candidates
                 inside that band around the true score; `fast_table` = ops.fast_table(ent_emb) to reuse
                 the split table across calls
+                "fast_exact": the tensor-core sweep with an a-priori error band around every true score; the few
+                candidates inside the band are re-scored in the reference's fp32 order (blp_rank_sweep_fast_exact), so
+                gt / ge / the filtered counters and every metric are bit-identical to "exact" at close to "fast" speed.
+                If more candidates fall into the band than the worklist holds (degenerate tables: identical rows),
+                the sweep is transparently redone in "exact" mode (`out["refine_overflow"]` tells); checking that
+                costs one device synchronisation per sweep
     sort_by_relation   exact mode, D = 128, sweeps of >= 64 M scores per direction: process the triples in relation-aligned order (AlignedTriples)
                 (one stable argsort per sweep; the outputs come back in the caller's order).  Triples that share a relation let the kernel compute
                 fl(candidate + r) once for several head-prediction queries (~13 % fewer FP32 lane-ops); results are
@@ -174,6 +180,7 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
     mrr / hits_at_k (and mrr_f / hits_at_k_f) python floats normalised by 2T (train.py:196-200).
     """
     dev = ent_emb.device
+    triples_in, h_rows_in, t_rows_in = triples, h_rows, t_rows         # as passed (the fast_exact overflow fallback re-runs them)
     aligned = triples if isinstance(triples, AlignedTriples) else None
     if aligned is not None:
         triples = aligned.padded
@@ -203,8 +210,11 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         # native path: the train.py:141-143 gathers run inside the kernels, results land in (2, T) arrays
         if triples.dtype != torch.int64 or not triples.is_contiguous():
             triples = triples.to(torch.int64).contiguous()
-        if mode not in ("exact", "fast"):
+        if mode not in ("exact", "fast", "fast_exact"):
             raise ValueError(f"unknown mode {mode!r}")
+        refine = mode == "fast_exact"
+        if refine:
+            mode = "fast"
         # worth one sort + a few small gathers only when the sweep itself is milliseconds long
         if (aligned is None and sort_by_relation and mode == "exact"
                 and (not filtered or dev_index is not None) and ent_emb.shape[1] == 128
@@ -223,6 +233,8 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         if mode == "fast" and fast_table is None:
             fast_table = ops.fast_table(ent_emb)
             launches += 1
+        # filter + refine: room for 64 band candidates per query of a chunk (a handful are expected)
+        refine_ws = ops.refine_workspace(dev, max(1 << 16, 128 * min(T, chunk))) if refine and T > 0 else None
         # one allocation: the int32 counters, then the fp32 true scores
         buf = torch.empty((len(names) + 1, 2, T), dtype=torch.int32, device=dev)
         counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
@@ -267,7 +279,8 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 launches += ops.rank_sweep_chunk(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
                                                  None if h_rows is None else h_rows[lo:hi],
                                                  None if t_rows is None else t_rows[lo:hi], indptr, idx, ent_offset,
-                                                 fast_table_ws=fast_table if mode == "fast" else None, counts_only=split)
+                                                 fast_table_ws=fast_table if mode == "fast" else None, counts_only=split,
+                                                 refine_ws=refine_ws)
                 if dev_index is not None:
                     launches += ops.filter_correct(rel_model, ent_emb, rel_weight.detach(), triples, outs, lo, hi,
                                                    dev_index.workspace, dev_index.num_edges, dev_index.num_rows,
@@ -278,6 +291,20 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
                 join = torch.cuda.Event()
                 join.record(s_)
                 main.wait_event(join)
+        if refine_ws is not None:
+            overflow = refine_ws[:8].view(torch.int32)[1:2].clone()
+            if world > 1:
+                _dist().all_reduce(overflow, op=_dist().ReduceOp.MAX, group=group)   # every rank takes the same branch
+            if int(overflow) != 0:
+                # more band candidates than the worklist holds: the counters are incomplete -- redo the sweep exactly
+                out = rank_sweep(rel_model, ent_emb, rel_weight, triples_in, filter_index=filter_index,
+                                 filter_triples=filter_triples, filter_csr=filter_csr, k_values=k_values,
+                                 ent_offset=ent_offset, group=group, chunk=chunk, group_triples=group_triples,
+                                 h_rows=h_rows_in, t_rows=t_rows_in, mode="exact", sort_by_relation=sort_by_relation,
+                                 overlap_chunks=overlap_chunks)
+                out["refine_overflow"] = True
+                out["launches"] += launches
+                return out
         if aligned is not None:
             # back to the caller's order (padding entries are dropped)
             buf = buf.index_select(2, aligned.dest)
@@ -345,7 +372,7 @@ class RankSweepPlan:
         dev = ops._require_cuda(ent_emb, rel_weight)
         if ent_emb.dtype != torch.float32 or not ent_emb.is_contiguous() or ent_emb.dim() != 2:
             raise ValueError("ent_emb must be a contiguous fp32 (N, D) tensor")
-        if mode not in ("exact", "fast"):
+        if mode not in ("exact", "fast", "fast_exact"):
             raise ValueError(f"unknown mode {mode!r}")
         if filter_index is not None and not hasattr(filter_index, "workspace"):
             raise ValueError("RankSweepPlan takes a utils.DeviceFilterIndex (built once per evaluation)")
@@ -373,9 +400,16 @@ class RankSweepPlan:
                 self.out["sums" + suffix] = torch.zeros(1 + len(ks), dtype=torch.float64, device=dev)
             self.fast_table = None
             self._qws = None
-            if mode == "fast":
+            self._refine = None
+            if mode in ("fast", "fast_exact"):
                 self.fast_table = fast_table if fast_table is not None else ops.fast_table(ent_emb)
                 self._qws = torch.empty(int(lib.blp_fast_query_bytes(T)), dtype=torch.uint8, device=dev)
+            if mode == "fast_exact":
+                # worklist of the refine pass; out["refine_state"] = [entries of the last call, sticky overflow flag]:
+                # a non-zero flag (check it once, after the last batch: plan.refine_overflowed()) invalidates the
+                # batches since the plan was created -- re-run them with mode="exact"
+                self._refine = ops.refine_workspace(dev, max(1 << 16, 128 * T))
+                self.out["refine_state"] = self._refine[:8].view(torch.int32)
         p = ops._ptr
         o = self.out
         # the raw metrics come out of the sweep launch itself on a single GPU (exact mode); sharded sweeps reduce
@@ -397,10 +431,16 @@ class RankSweepPlan:
         self._tail = (None, None, T, p(o["gt"]), p(o["ge"]), None, None, p(o["true_score"]))
         if mode == "fast":
             self._tail = self._tail + (p(self.fast_table), p(self._qws), None, n)
+        elif mode == "fast_exact":
+            self._tail = self._tail + (p(self.fast_table), p(self._qws), p(self._refine), int(self._refine.refine_capacity))
         self._lib = lib
         for suffix in ("", "_f") if self.filtered else ("",):
             o["hits" + suffix + "_bool"] = o["hits" + suffix].view(torch.bool)
         self.launches = 0
+
+    def refine_overflowed(self):
+        """fast_exact mode: did any call since the plan was created drop band candidates (device sync)?"""
+        return self._refine is not None and int(self.out["refine_state"][1]) != 0
 
     def __del__(self):
         plan, self._plan = getattr(self, "_plan", None), None
@@ -429,6 +469,9 @@ class RankSweepPlan:
                     ops.check(lib.blp_plan_run(self._plan, triples.data_ptr(), ops._ptr(h_rows), ops._ptr(t_rows), stream),
                               "blp_plan_run")
                     raw_metrics_done = self._fused_metrics
+                elif self._refine is not None:
+                    ops.check(lib.blp_rank_sweep_fast_exact(*self._head, triples.data_ptr(), T, ops._ptr(h_rows),
+                                                            ops._ptr(t_rows), *self._tail, stream), "blp_rank_sweep_fast_exact")
                 else:
                     ops.check(lib.blp_rank_sweep_fast(*self._head, triples.data_ptr(), T, ops._ptr(h_rows), ops._ptr(t_rows),
                                                       *self._tail, stream), "blp_rank_sweep_fast")

@@ -240,6 +240,16 @@ def fast_table(ent):
     return ws
 
 
+def refine_workspace(dev, capacity):
+    """Worklist of the filter + refine mode (blp_rank_sweep_fast_exact): zeroed header {count, overflow} + `capacity`
+    (query, candidate) pairs.  view(int32)[0] = entries of the last call, [1] = sticky overflow flag."""
+    capacity = int(capacity)
+    ws = torch.empty(int(lib().blp_fast_refine_bytes(capacity)), dtype=torch.uint8, device=dev)
+    ws[:16].zero_()
+    ws.refine_capacity = capacity
+    return ws
+
+
 def true_scores(model, ent, rel_weight, triples, out, h_rows=None, t_rows=None, ent_offset=0):
     """blp_true_scores: true-triple scores + counter reset for ALL triples of a chunked sweep, one launch."""
     mid = model_id(model)
@@ -259,7 +269,8 @@ def true_scores(model, ent, rel_weight, triples, out, h_rows=None, t_rows=None, 
 
 
 def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, t_rows=None, filt_indptr=None,
-                     filt_idx=None, ent_offset=0, fast_table_ws=None, scores_out=None, counts_only=False):
+                     filt_idx=None, ent_offset=0, fast_table_ws=None, scores_out=None, counts_only=False,
+                     refine_ws=None):
     """blp_rank_sweep on triples[lo:hi], written straight into the (2, T) arrays of `out`.
 
     triples (T, 3) int64 contiguous on the device: (head row, tail row, relation id); `out` holds
@@ -307,6 +318,11 @@ def rank_sweep_chunk(model, ent, rel_weight, triples, out, lo, hi, h_rows=None, 
                 check(lib().blp_rank_sweep_counts(*common, stream), "blp_rank_sweep_counts")
             elif fast_table_ws is None:
                 check(lib().blp_rank_sweep(*common, stream), "blp_rank_sweep")
+            elif refine_ws is not None:
+                # tensor-core sweep + exact refine of the band around the true score: the exact mode's integer counters
+                qws = torch.empty(int(lib().blp_fast_query_bytes(b)), dtype=torch.uint8, device=dev)
+                check(lib().blp_rank_sweep_fast_exact(*common, _ptr(fast_table_ws), _ptr(qws), _ptr(refine_ws),
+                                                      int(refine_ws.refine_capacity), stream), "blp_rank_sweep_fast_exact")
             else:
                 # tensor-core mode (distmult / complex / simple, d = 128): tolerance-classified parity
                 qws = torch.empty(int(lib().blp_fast_query_bytes(b)), dtype=torch.uint8, device=dev)

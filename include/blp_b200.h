@@ -203,6 +203,31 @@ int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local, int64_t en
                         const void *table_ws, void *query_ws, float *scores_out, int64_t ld_scores,
                         void *stream);
 
+/* ---- exact ranks on the tensor path: filter + refine (distmult / complex / simple, d = 128) ----
+ * blp_rank_sweep_fast with an a-priori error band around the true score.  The fold kernel derives, per query,
+ *   band = kappa * || |folded coefficients| ||_2 * max_e ||e||_2      (kappa = 2e-5, scaled like the accumulator)
+ * which bounds |fast score - reference fp32 score| for every candidate (Cauchy-Schwarz over sum|terms|; the
+ * reference's own rounding, the fold, the split and the tensor-core accumulation are each <= ~8e-6 * sum|terms|,
+ * DESIGN.md 4.2b).  The sweep kernel counts only candidates that beat the true score by more than the band; the
+ * few candidates inside the band (a handful per query) are appended to a worklist and re-scored by a refine
+ * kernel with the reference's fp32 operations in the reference's summation order (models.py:226-248), the same
+ * code that produces the true-triple scores.  gt / ge (and the filtered counters) are then bit-identical to
+ * blp_rank_sweep (exact mode) -- the integer ranks of the reference -- at tensor-core speed.
+ *   refine_ws        blp_fast_refine_bytes(refine_capacity) bytes; the first 16 bytes are a header
+ *                    {uint32 count; uint32 overflow; ...}: ZERO it once before the first call.  `overflow` is
+ *                    sticky: non-zero after a call means more than refine_capacity candidates fell into the band
+ *                    (e.g. a table of identical rows) and the counters of that call are NOT valid -- re-run the
+ *                    chunk with blp_rank_sweep.  `count` holds the entries of the last call.
+ *   ent, rel_weight, h_rows, t_rows must be 16-byte aligned.  Other arguments as blp_rank_sweep_fast. */
+int64_t blp_fast_refine_bytes(int64_t refine_capacity);
+int blp_rank_sweep_fast_exact(int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
+                              const float *rel_weight, int64_t num_rel, const int64_t *triples, int64_t t,
+                              const float *h_rows, const float *t_rows,
+                              const int64_t *filt_indptr, const int64_t *filt_idx, int64_t tail_off,
+                              int32_t *gt, int32_t *ge, int32_t *gt_f, int32_t *ge_f, float *true_score,
+                              const void *table_ws, void *query_ws, void *refine_ws, int64_t refine_capacity,
+                              void *stream);
+
 /* utils.py:106-109 + train.py:154-157 in one launch: per-query reciprocal ranks / hits
  * (either may be NULL) and the fp64 accumulators of blp_metrics_reduce. */
 int blp_rank_metrics(const int32_t *gt, const int32_t *ge, int64_t q, const int64_t *k_values_host, int nk,

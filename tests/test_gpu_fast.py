@@ -138,3 +138,123 @@ def test_fast_filtered_counters_stay_valid_with_tied_filtered_candidates(model, 
         band = np.array([(np.abs(ent_np - ent_np[int(t)]).max(axis=1) == 0).sum() - 1 for t in true_rows])
         assert bool(((fast["ge_f"][role].cpu() - exact["ge_f"][role].cpu()).abs().numpy() <= band).all())
         assert bool(((fast["gt_f"][role].cpu() - exact["gt_f"][role].cpu()).abs().numpy() <= band).all())
+
+
+# ---- filter + refine: the tensor-core sweep with exact integer ranks (blp_rank_sweep_fast_exact) ----------------------
+def _assert_same_counters(a, b, names=("gt", "ge")):
+    assert torch.equal(a["true_score"], b["true_score"])
+    for k in names:
+        assert torch.equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()))
+
+
+@pytest.mark.parametrize("model", FAST_MODELS)
+@pytest.mark.parametrize("n,b", [(128, 64), (700, 37), (1000, 64), (5000, 100), (131, 1), (14541, 300)])
+def test_fast_exact_counters_equal_oracle(model, n, b, cuda_device):
+    """gt / ge of the filter + refine mode are the oracle's integers (bit-exact ranks on the tensor path)."""
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=3 * n + b, n_rel=23)
+    dev = cuda_device
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    out = blp_b200.rank_sweep(model, ent.to(dev), rel.to(dev), triples, mode="fast_exact")
+    assert "refine_overflow" not in out
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(),
+                            heads.numpy(), tails.numpy())
+    assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+    assert np.array_equal(out["gt"].reshape(-1).cpu().numpy(), co["gt"])
+    assert np.array_equal(out["ge"].reshape(-1).cpu().numpy(), co["ge"])
+
+
+@pytest.mark.parametrize("model,n,b", [("distmult", 14541, 2048), ("complex", 40943, 1024), ("simple", 14541, 1024)])
+def test_fast_exact_equals_exact_mode_at_benchmark_sizes(model, n, b, cuda_device):
+    """FB15k-237 / WN18RR-sized tables: every counter and metric of the two modes is identical, and the band the refine
+    pass had to re-score is a handful of candidates per query."""
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=5, n_rel=237)
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    exact = blp_b200.rank_sweep(model, e, r, triples)
+    plan = blp_b200.RankSweepPlan(model, e, r, b, mode="fast_exact")
+    fx = plan(triples)
+    _assert_same_counters(exact, fx)
+    assert torch.equal(exact["recip"].reshape(-1), fx["recip"].reshape(-1))
+    assert torch.equal(exact["sums"][1:], fx["sums"][1:])                                  # hit counts
+    assert abs(float(exact["sums"][0]) - float(fx["sums"][0])) <= 1e-12 * float(exact["sums"][0])   # fp64 sum order differs
+    assert not plan.refine_overflowed()
+    per_query = int(fx["refine_state"][0]) / (2 * b)
+    assert 1.0 <= per_query <= 64.0, per_query          # >= 1: the true entity itself is always inside the band
+    # and through rank_sweep (chunked, its own worklist)
+    fx2 = blp_b200.rank_sweep(model, e, r, triples, mode="fast_exact", chunk=300)
+    _assert_same_counters(exact, fx2)
+
+
+@pytest.mark.parametrize("model", FAST_MODELS)
+def test_fast_exact_with_ties_duplicates_and_filters(model, cuda_device):
+    """Duplicated rows tie with the true score bit for bit: they land in the band, the refine pass re-scores them with
+    the reference's operations and the raw AND filtered counters equal the exact mode's (no clamping involved)."""
+    n, b, n_rel = 400, 24, 5
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=78, n_rel=n_rel)
+    heads, tails = heads % 300, tails % 300
+    edges = []
+    for i in range(b):
+        ent[300 + i] = ent[heads[i]]
+        ent[330 + i] = ent[tails[i]]
+        edges += [(300 + i, int(tails[i]), int(rels[i])), (int(heads[i]), 330 + i, int(rels[i]))]
+    ent[360:380] = 0.0                                       # zero rows: score exactly 0
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    fidx = blp_b200.DeviceFilterIndex(np.array(edges, np.int64), None, n, n_rel, dev)
+    exact = blp_b200.rank_sweep(model, e, r, triples, filter_index=fidx)
+    fx = blp_b200.rank_sweep(model, e, r, triples, filter_index=fidx, mode="fast_exact")
+    _assert_same_counters(exact, fx, ("gt", "ge", "gt_f", "ge_f"))
+    assert torch.equal(exact["sums_f"][1:], fx["sums_f"][1:])
+    assert abs(float(exact["sums_f"][0]) - float(fx["sums_f"][0])) <= 1e-12 * float(exact["sums_f"][0])
+
+
+def test_fast_exact_shard_sums_equal_exact_full_table(cuda_device):
+    model, n, b = "complex", 3000, 50
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=29)
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    exact = blp_b200.rank_sweep(model, e, r, triples)
+    acc = {k: torch.zeros_like(exact[k]) for k in ("gt", "ge")}
+    for rank in range(3):
+        lo, hi = blp_b200.shard_bounds(n, 3, rank)
+        part = blp_b200.rank_sweep(model, e[lo:hi].contiguous(), r, triples, mode="fast_exact", ent_offset=lo,
+                                   h_rows=e[triples[:, 0]], t_rows=e[triples[:, 1]])
+        for k in acc:
+            acc[k] += part[k]
+    for k in acc:
+        assert torch.equal(acc[k], exact[k]), k
+
+
+def test_fast_exact_band_bounds_the_observed_error(cuda_device):
+    """The a-priori band (kappa = 2e-5 of ||fold_abs|| * max||e||) against the measured |fast - reference| on random
+    data: the observed maximum must stay below a quarter of it (margin for other data)."""
+    for model in FAST_MODELS:
+        n, b = 5000, 64
+        ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=101)
+        out, scores = _run_fast(model, ent, rel, heads, tails, rels, cuda_device)
+        h, t, r = ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy()
+        co = c_oracle.eval_rank(model, ent.numpy(), h, t, r, heads.numpy(), tails.numpy(), want_scores=True)
+        err = np.abs(scores.cpu().numpy().astype(np.float64) - co["scores"].astype(np.float64)).max(axis=1)
+        _, mass = np_oracle.fast_mode_reference(model, ent.numpy(), h, t, r)        # sum|terms| per (query, candidate)
+        # the band is relative to a Cauchy-Schwarz bound >= mass.max(axis=1)
+        assert (err <= 0.25 * 2e-5 * mass.max(axis=1) + 1e-30).all(), (model, float((err / mass.max(axis=1)).max()))
+
+
+def test_fast_exact_overflow_falls_back_to_exact(cuda_device):
+    """A table of identical rows puts EVERY candidate into the band: the worklist overflows, the flag is raised and
+    rank_sweep redoes the sweep in exact mode (same results, `refine_overflow` reported)."""
+    model, n, b = "distmult", 70000, 8
+    ent, rel, heads, tails, rels = make_inputs(model, 64, 128, b, seed=7)
+    ent = ent[:1].repeat(n, 1).contiguous()
+    heads, tails = heads % n, tails % n
+    dev = cuda_device
+    e, r = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    exact = blp_b200.rank_sweep(model, e, r, triples)
+    fx = blp_b200.rank_sweep(model, e, r, triples, mode="fast_exact")        # 2 * 8 * 70000 band entries > capacity 65536
+    assert fx.get("refine_overflow") is True
+    _assert_same_counters(exact, fx)
+    assert int(exact["ge"].min()) == n and int(exact["gt"].max()) == 0

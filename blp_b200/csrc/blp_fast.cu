@@ -331,6 +331,13 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
     }
 }
 
+// unused tail [pos, end) of a warp's worklist block: skip entries
+constexpr int kRefineBlock = 128;
+__device__ __forceinline__ void refine_pad(const FastArgs &args, unsigned int pos, unsigned int end, int lane) {
+    for (unsigned int p = pos + (unsigned int)lane; p < end; p += 32u)
+        if ((long long)p < args.refine_cap) args.refine->entries[p] = make_int2(-1, 0);
+}
+
 // ---- the sweep --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs args, const __grid_constant__ CUtensorMap tm_q,
                                                                   const __grid_constant__ CUtensorMap tm_e) {
@@ -452,6 +459,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
 #pragma unroll
         for (int h = 0; h < kFH; ++h) { slot[h] = -1; self_local[h] = -1; th[h] = 0.f; inv[h] = 1.f; bd[h] = 0.f; valid_q[h] = false; cgt[h] = cge[h] = 0; }
         uint32_t it = 0;
+        unsigned int wl_pos = 0u, wl_end = 0u;                           // this warp's block of worklist slots (refine mode)
         auto flush = [&]() {
 #pragma unroll
             for (int h = 0; h < kFH; ++h) {
@@ -508,11 +516,12 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                         for (int c = 0; c < 32; ++c)
                             if (ch * 32 + c < nvalid) orow[c] = fmul(__uint_as_float(v[c]), inv[h]);
                     }
+                    // plain fast mode: bd == 0, both thresholds are the scaled true score.  Refine mode: `gs` counts the
+                    // candidates that beat the true score for certain (s > st + band), `es` those that may tie or beat
+                    // it (s >= st - band); the difference is the band, which goes to the worklist
+                    const float st_hi = st + bd[h], st_lo = st - bd[h];
+                    int gs = 0, es = 0;
                     if (valid_q[h]) {
-                        // plain fast mode: bd == 0, both thresholds are the scaled true score.  Refine mode: `g` counts the
-                        // candidates that beat the true score for certain (s > st + band), `e` those that may tie or beat
-                        // it (s >= st - band); the difference is the band, which goes to the worklist
-                        const float st_hi = st + bd[h], st_lo = st - bd[h];
                         int g[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};    // independent chains
                         if (nvalid == kFN) {
 #pragma unroll
@@ -530,30 +539,72 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                                 e[c & 3] += ok && s >= st_lo;
                             }
                         }
-                        int gs = (g[0] + g[1]) + (g[2] + g[3]), es = (e[0] + e[1]) + (e[2] + e[3]);
-                        if (args.refine) {
-                            if (es != gs) {                              // rare: a few candidates per query and sweep
-#pragma unroll
-                                for (int c = 0; c < 32; ++c) {
-                                    const float s = __uint_as_float(v[c]);
-                                    if (ch * 32 + c < nvalid && s >= st_lo && !(s > st_hi)) {
-                                        const unsigned int at = atomicAdd(&args.refine->count, 1u);
-                                        if ((long long)at < args.refine_cap)
-                                            args.refine->entries[at] = make_int2((int)q, (int)(tile_base + ch * 32 + c));
-                                    }
-                                }
-                            }
-                            es = gs;                                     // the refine kernel adds the band's exact verdicts
-                        } else if (self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
+                        gs = (g[0] + g[1]) + (g[2] + g[3]);
+                        es = (e[0] + e[1]) + (e[2] + e[3]);
+                        if (!args.refine && self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
                             // the true entity itself: it ties with s_true by definition (utils.py:104-105), whatever
                             // the fast arithmetic produced for it
                             const float s_self = __uint_as_float(select32(v, (int)(self_col & 31)));
                             gs -= s_self > st;
                             es += 1 - (s_self >= st);
                         }
-                        cgt[h] += gs;
-                        cge[h] += es;
                     }
+                    if (args.refine) {                                   // warp-uniform
+                        // The band of this 32-column chunk goes to the worklist.  Slots are handed out warp-wide: the
+                        // warp owns a block of kRefineBlock entries (ONE global atomic per block -- a returning atomic
+                        // per entry on a single address serialises the whole chip: 0.33 -> 1.1 ms per 16,384 triples),
+                        // a ballot ranks the lanes that append at the same column; what is left of a block is padded
+                        // with skip entries (q = -1).
+                        const bool mine = es != gs;
+                        if (__any_sync(0xffffffffu, mine)) {             // ~1 chunk visit in 5 at 3 band candidates per query
+                            // per-lane bit mask of the band columns (branch-free, small), then a ROLLED loop over the
+                            // columns that have a band candidate in any lane -- usually one.  (Unrolling the append 32
+                            // times made this rare path ~50 KB of code: every visit thrashed the instruction cache,
+                            // 3 -> 17 us per work item.)
+                            unsigned int bm = 0u;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float s = __uint_as_float(v[c]);
+                                bm |= (s >= st_lo && !(s > st_hi)) ? (1u << c) : 0u;
+                            }
+                            if (!mine) bm = 0u;
+                            const int left = nvalid - ch * 32;           // valid columns of this chunk
+                            if (left < 32) bm &= left <= 0 ? 0u : ((1u << left) - 1u);
+                            unsigned int cols = __reduce_or_sync(0xffffffffu, bm);
+#pragma unroll 1
+                            while (cols) {
+                                const int c = __ffs((int)cols) - 1;
+                                cols &= cols - 1u;
+                                const bool in = (bm >> c) & 1u;
+                                const unsigned int mask = __ballot_sync(0xffffffffu, in);
+                                const unsigned int k = (unsigned int)__popc(mask);
+                                if (wl_pos + k > wl_end) {
+                                    refine_pad(args, wl_pos, wl_end, lane);
+                                    unsigned int base = 0u;
+                                    if (lane == 0) {
+                                        // far past any capacity (< 2^31): stop counting so the 32-bit counter cannot wrap
+                                        if (*reinterpret_cast<volatile unsigned int *>(&args.refine->count) >= 0xC0000000u) {
+                                            args.refine->overflow = 1u;
+                                            base = 0xC0000000u;
+                                        } else {
+                                            base = atomicAdd(&args.refine->count, (unsigned int)kRefineBlock);
+                                        }
+                                    }
+                                    wl_pos = __shfl_sync(0xffffffffu, base, 0);
+                                    wl_end = wl_pos + kRefineBlock;
+                                }
+                                if (in) {
+                                    const unsigned int at = wl_pos + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+                                    if ((long long)at < args.refine_cap)
+                                        args.refine->entries[at] = make_int2((int)q, (int)(tile_base + ch * 32 + c));
+                                }
+                                wl_pos += k;
+                            }
+                        }
+                        es = gs;                                         // the refine kernel adds the band's exact verdicts
+                    }
+                    cgt[h] += gs;
+                    cge[h] += es;
                 }
             }
             tc_fence_before();
@@ -561,6 +612,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
             if (lane == 0) mbar_arrive(&sm.d_empty[buf]);
         }
         flush();
+        if (args.refine) refine_pad(args, wl_pos, wl_end, lane);
     }
 
     tc_fence_before();
@@ -588,15 +640,14 @@ __global__ void __launch_bounds__(kRefineWarps * 32) refine_kernel(RefineList *_
     if (blockIdx.x == 0 && threadIdx.x == 0 && (long long)count > cap) wl->overflow = 1u;   // entries were dropped: results invalid
     const long long stride = (long long)gridDim.x * kRefineWarps * 4;
     for (long long base = ((long long)blockIdx.x * kRefineWarps + warp) * 4; base < n; base += stride) {
-        const int nj = (int)(n - base < 4 ? n - base : 4);
         const float *h[4], *t[4], *r[4];
         long long slot[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            h[u] = t[u] = r[u] = ent;
+            h[u] = t[u] = r[u] = ent;                                      // idle job (past the end / skip entry): any valid row
             slot[u] = -1;
-            if (u < nj) {
-                const int2 e = wl->entries[base + u];
+            const int2 e = base + u < n ? wl->entries[base + u] : make_int2(-1, 0);
+            if (e.x >= 0) {
                 const long long q = e.x;
                 const bool head_pred = q < b;
                 const long long i = head_pred ? q : q - b;
@@ -607,10 +658,11 @@ __global__ void __launch_bounds__(kRefineWarps * 32) refine_kernel(RefineList *_
                 r[u] = rr.row(i, kD);
             }
         }
-        const float s = true_scores_warp128x4<MODEL>(h, t, r, nj, tm[warp], lane);
+        if (slot[0] < 0 && slot[1] < 0 && slot[2] < 0 && slot[3] < 0) continue;     // warp-uniform: a padded block tail
+        const float s = true_scores_warp128x4<MODEL>(h, t, r, 4, tm[warp], lane);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (u < nj && lane == true_job_lane<MODEL>(u)) {
+            if (slot[u] >= 0 && lane == true_job_lane<MODEL>(u)) {
                 const float st = true_score[slot[u]];
                 if (s > st) atomicAdd(gt + slot[u], 1);
                 if (s >= st) atomicAdd(ge + slot[u], 1);

@@ -233,8 +233,9 @@ def rank_sweep(rel_model, ent_emb, rel_weight, triples, *, filter_index=None, fi
         if mode == "fast" and fast_table is None:
             fast_table = ops.fast_table(ent_emb)
             launches += 1
-        # filter + refine: room for 64 band candidates per query of a chunk (a handful are expected)
-        refine_ws = ops.refine_workspace(dev, max(1 << 16, 128 * min(T, chunk))) if refine and T > 0 else None
+        # filter + refine: room for 64 band candidates per query of a chunk (a handful are expected), and never less
+        # than the one block of 128 slots every epilogue warp of the grid reserves (148 x 8 x 128 = 151,552)
+        refine_ws = ops.refine_workspace(dev, max(1 << 19, 128 * min(T, chunk))) if refine and T > 0 else None
         # one allocation: the int32 counters, then the fp32 true scores
         buf = torch.empty((len(names) + 1, 2, T), dtype=torch.int32, device=dev)
         counters, true_score = buf[:len(names)], buf[len(names)].view(torch.float32)
@@ -408,7 +409,7 @@ class RankSweepPlan:
                 # worklist of the refine pass; out["refine_state"] = [entries of the last call, sticky overflow flag]:
                 # a non-zero flag (check it once, after the last batch: plan.refine_overflowed()) invalidates the
                 # batches since the plan was created -- re-run them with mode="exact"
-                self._refine = ops.refine_workspace(dev, max(1 << 16, 128 * T))
+                self._refine = ops.refine_workspace(dev, max(1 << 19, 128 * T))
                 self.out["refine_state"] = self._refine[:8].view(torch.int32)
         p = ops._ptr
         o = self.out

@@ -213,6 +213,9 @@ int blp_rank_sweep_fast(int model, const float *ent, int64_t n_local, int64_t en
  * kernel with the reference's fp32 operations in the reference's summation order (models.py:226-248), the same
  * code that produces the true-triple scores.  gt / ge (and the filtered counters) are then bit-identical to
  * blp_rank_sweep (exact mode) -- the integer ranks of the reference -- at tensor-core speed.
+ *   refine_capacity  worklist slots.  Every epilogue warp of the grid reserves slots in blocks of 128 (one global
+ *                    atomic per block), so allow SMs x 8 x 128 (151,552 on a B200) on top of the expected band
+ *                    (a few candidates per query); 2^19 + 128 t is a comfortable choice.
  *   refine_ws        blp_fast_refine_bytes(refine_capacity) bytes; the first 16 bytes are a header
  *                    {uint32 count; uint32 overflow; ...}: ZERO it once before the first call.  `overflow` is
  *                    sticky: non-zero after a call means more than refine_capacity candidates fell into the band

@@ -1,5 +1,5 @@
 """Run a few fused eval sweeps (for ncu captures and quick timing):
-    python tools/run_sweep.py [model] [E] [N] [reps] [exact|fast]
+    python tools/run_sweep.py [model] [E] [N] [reps] [exact|fast|fast_exact]
 E test triples (2E queries) are ranked against N candidates per call through blp_rank_sweep[_fast]."""
 import os
 import sys
@@ -27,11 +27,12 @@ if os.environ.get("SORT_REL"):
     triples = triples[torch.argsort(triples[:, 2], stable=True)].contiguous()
 out = {k: torch.empty((2, E), dtype=torch.int32, device=dev) for k in ("gt", "ge")}
 out["true_score"] = torch.empty((2, E), dtype=torch.float32, device=dev)
-ws = ops.fast_table(ent) if mode == "fast" else None
+ws = ops.fast_table(ent) if mode.startswith("fast") else None
+rws = ops.refine_workspace(dev, max(1 << 19, 128 * E)) if mode == "fast_exact" else None
 
 
 def call():
-    return ops.rank_sweep_chunk(model, ent, rel, triples, out, 0, E, fast_table_ws=ws)
+    return ops.rank_sweep_chunk(model, ent, rel, triples, out, 0, E, fast_table_ws=ws, refine_ws=rws)
 
 
 for _ in range(3):
@@ -46,4 +47,5 @@ torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 alg = N * 128 * 4 + E * 3 * 128 * 4 + 2 * E * 12
 print(f"{model} {mode} E={E} N={N}: {ms:.4f} ms per rank_sweep call, {2 * E * N / ms / 1e6:.2f} G scores/s, "
-      f"{alg / ms / 1e6:.1f} GB/s algorithmic, gt[0]={int(out['gt'][0, 0])}")
+      f"{alg / ms / 1e6:.1f} GB/s algorithmic, gt[0]={int(out['gt'][0, 0])}"
+      + (f", refine entries {int(rws[:8].view(torch.int32)[0])} overflow {int(rws[:8].view(torch.int32)[1])}" if rws is not None else ""))

@@ -108,6 +108,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of the (converged) warp; the same lane every time, so a commit follows the MMAs of its own thread
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // mbarrier arrive once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -404,32 +414,37 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = umma_idesc_f16(kFM, kFN);
-            long long cur_m = -1;
-            uint32_t a_use = 0, kbit = 0, it = 0;
-            int halves = kFH;
-            for (long long id = id_begin; id < id_end; ++id, ++it) {
-                const long long m = id / args.n_tiles;
-                if (m != cur_m) {
-                    mbar_wait(&sm.a_full, a_use & 1u);
-                    ++a_use;
-                    cur_m = m;
-                    halves = halves_of(m);
-                }
-                const uint32_t buf = it % kFBufs, duse = it / kFBufs;
-                mbar_wait(&sm.d_empty[buf], (duse & 1u) ^ 1u);          // epilogue has drained these accumulators
+        // ===================== MMA issuer =====================
+        // The WHOLE warp runs this loop in convergent code and one elected lane issues the tcgen05 instructions: every
+        // operand (descriptors, TMEM addresses) is then provably warp-uniform and lives in uniform registers.  With the
+        // loop under `if (lane == 0)` ptxas had to move each operand into a uniform register through an ELECT /
+        // R2UR.BROADCAST / BRA.U.ANY waterfall -- 13 dependent instructions in front of every UTCHMMA, 118 clocks per
+        // MMA issued against the 64-clock floor of an M128 x N128 x K16 MMA (profiles/r02_fast_kernel_experiments.txt).
+        constexpr uint32_t idesc = umma_idesc_f16(kFM, kFN);
+        long long cur_m = -1;
+        uint32_t a_use = 0, kbit = 0, it = 0;
+        int halves = kFH;
+        for (long long id = id_begin; id < id_end; ++id, ++it) {
+            const long long m = id / args.n_tiles;
+            if (m != cur_m) {
+                mbar_wait(&sm.a_full, a_use & 1u);
+                ++a_use;
+                cur_m = m;
+                halves = halves_of(m);
+            }
+            const uint32_t buf = it % kFBufs, duse = it / kFBufs;
+            mbar_wait(&sm.d_empty[buf], (duse & 1u) ^ 1u);          // epilogue has drained these accumulators
+            tc_fence_after();
+            for (int kb = 0; kb < 2; ++kb, ++kbit) {
+                const int stage = kbit % kFStages;
+                const uint32_t use = kbit / kFStages;
+                mbar_wait(&sm.b_full[stage], use & 1u);
                 tc_fence_after();
-                for (int kb = 0; kb < 2; ++kb, ++kbit) {
-                    const int stage = kbit % kFStages;
-                    const uint32_t use = kbit / kFStages;
-                    mbar_wait(&sm.b_full[stage], use & 1u);
-                    tc_fence_after();
-                    const uint64_t b_hi = umma_smem_desc(&sm.b[stage][0][0]), b_lo = umma_smem_desc(&sm.b[stage][1][0]);
-                    for (int half = 0; half < ((args.debug & 4) ? 0 : halves); ++half) {   // the candidate k-block serves both query halves
-                        const uint32_t d_tmem = tmem + buf * (kFH * kFN) + half * kFN;
-                        const uint64_t a_hi = umma_smem_desc(&sm.a[half][0][kb][0]), a_lo = umma_smem_desc(&sm.a[half][1][kb][0]);
+                const uint64_t b_hi = umma_smem_desc(&sm.b[stage][0][0]), b_lo = umma_smem_desc(&sm.b[stage][1][0]);
+                for (int half = 0; half < ((args.debug & 4) ? 0 : halves); ++half) {   // the candidate k-block serves both query halves
+                    const uint32_t d_tmem = tmem + buf * (kFH * kFN) + half * kFN;
+                    const uint64_t a_hi = umma_smem_desc(&sm.a[half][0][kb][0]), a_lo = umma_smem_desc(&sm.a[half][1][kb][0]);
+                    if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < kFKB / 16; ++ks) {        // 16 halves = 32 bytes = 2 descriptor units per step
                             const uint64_t o = (uint64_t)(ks * 2);
@@ -438,13 +453,17 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                             umma_f16(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
                         }
                     }
-                    umma_commit(&sm.b_empty[stage]);                    // frees the stage once these MMAs have read it
+                    __syncwarp();
                 }
+                if (elect_one()) umma_commit(&sm.b_empty[stage]);   // frees the stage once these MMAs have read it
+                __syncwarp();
+            }
+            if (elect_one()) {
                 umma_commit(&sm.d_full[buf]);
                 if (id + 1 == id_end || (id + 1) / args.n_tiles != m) umma_commit(&sm.a_empty);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue: one query row of each half per thread =====================
         // TMEM lane = query row; a warp can only read the lane quarter (warp % 4), so the two warps of a quarter

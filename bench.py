@@ -584,6 +584,18 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
                 state["launches"] = out["launches"]
                 return out
         ms = time_calls(call, reps=max(3, min(50, int(200 / max(1, e // 64)))), warm=2)
+        # the sweep kernel alone (CUDA events around its launch, blp_profile_events slot 1), median of 7 calls
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(7)]
+        for a_, b_ in evs:
+            a_.record(); b_.record()
+        torch.cuda.synchronize()
+        lib_ = ops.lib()
+        for a_, b_ in evs:
+            lib_.blp_profile_events(1, ctypes.c_void_p(a_.cuda_event), ctypes.c_void_p(b_.cuda_event))
+            call()
+        lib_.blp_profile_events(0, None, None)
+        torch.cuda.synchronize()
+        kern_ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)[len(evs) // 2]
         out = call()
         torch.cuda.synchronize()
         leg = {"config": f"synthetic {dataset} ({w['n']} entities) BLP-{model} dim={w['d']}, {mode} mode, {e} test triples per call, "
@@ -592,6 +604,13 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
                "sweep_s_all_test_triples": ms * 1e-3 * w["t"] / e, "mrr": float(out["sums"][0]) / (2 * e)}
         leg["roofline"] = sweep_roofline(model, mode, w["n"], w["d"], 2 * e, ms * 1e-3, peaks, fp32_peak, hbm_peak,
                                          {"timed": "whole call (all launches of the call), back to back"}, exec_ops=exec_ops)
+        if kern_ms > 0:
+            # the dominant kernel of the call on its own (fold / refine / metrics launches excluded)
+            kr = sweep_roofline(model, mode, w["n"], w["d"], 2 * e, kern_ms * 1e-3, peaks, fp32_peak, hbm_peak, exec_ops=exec_ops)
+            leg["roofline"]["sweep_kernel_ms"] = kern_ms
+            leg["roofline"]["sweep_kernel_frac"] = kr["frac"]
+            if "issued_frac" in kr:
+                leg["roofline"]["sweep_kernel_issued_frac"] = kr["issued_frac"]
         sums_of[name] = out["sums"].detach().cpu()
         if mode == "fast_exact":
             st = out["refine_state"].cpu()
@@ -977,6 +996,8 @@ def main_b200(args):
                 roofline[tag + "_frac"] = r["frac"]
                 if "issued_frac" in r:
                     roofline[tag + "_issued_frac"] = r["issued_frac"]
+                if "sweep_kernel_issued_frac" in r:
+                    roofline[tag + "_kernel_issued_frac"] = r["sweep_kernel_issued_frac"]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

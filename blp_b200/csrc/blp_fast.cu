@@ -54,11 +54,23 @@ constexpr int kFThreads = (4 + kFEpiWarps) * 32;
 constexpr int kTmemCols = 512;             // kFBufs buffers x 2 halves x kFN columns
 constexpr float kFTargetExp = 14.0f;       // operands are scaled so that max |x| <= 2^14 (fp16 max is 65504)
 
-struct __align__(1024) FastSmem {
-    __half a[kFH][2][2][kFBox];            // [query half][hi | lo][k-block] query block
-    __half b[kFStages][2][kFBoxB];         // [stage][hi | lo] candidate k-block
+// PAIR = a cluster of two CTAs running tcgen05.mma.cta_group::2 (M = 256: 128 query rows in each CTA's TMEM): every
+// CTA stages only HALF of each candidate k-block (64 of the 128 rows), so the shared-memory operand fetch of an MMA
+// drops from 8 KB to 6 KB per SM and the L2 -> SMEM candidate stream is halved; the ring gets twice the stages.
+template <bool PAIR>
+struct FastCfg {
+    static constexpr int kRowsB = PAIR ? kFN / 2 : kFN;      // candidate rows of a k-block staged by one CTA
+    static constexpr int kBoxB = kRowsB * kFKB;              // halves in one candidate TMA box
+    static constexpr int kStages = PAIR ? 2 * kFStages : kFStages;
+    static constexpr int kQ = (PAIR ? 2 : 1) * kFH * kFM;    // queries per work item (256, or 512 over the pair)
+};
+template <bool PAIR>
+struct __align__(1024) FastSmemT {
+    static constexpr int kStages = FastCfg<PAIR>::kStages;
+    __half a[kFH][2][2][kFBox];            // [query half][hi | lo][k-block] query block (this CTA's 256 queries)
+    __half b[kStages][2][FastCfg<PAIR>::kBoxB];   // [stage][hi | lo] candidate k-block (this CTA's rows of it)
     uint64_t a_full, a_empty;
-    uint64_t b_full[kFStages], b_empty[kFStages];
+    uint64_t b_full[kStages], b_empty[kStages];
     uint64_t d_full[kFBufs], d_empty[kFBufs];
     uint32_t tmem_base;
 };
@@ -84,6 +96,7 @@ struct FastArgs {
     int debug;                             // timing experiments (BLP_FAST_DEBUG): 1 = no epilogue work, 2 = no B loads, 4 = no MMAs
     // ---- exact ranks on the tensor path (filter + refine): candidates whose fast score lies within `band[q]` of the
     // scaled true score are not counted here but appended to the worklist and re-scored in the reference's fp32 order
+    int pair;                              // launched as CTA pairs (cta_group::2)
     const float *band;                     // [q_pad] a-priori bound on |fast - reference| in the scaled domain (NULL = plain fast mode)
     RefineList *refine;                    // worklist (header + entries)
     long long refine_cap;
@@ -108,6 +121,49 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA) . B (N / 2 rows from each CTA)^T; issued by the leader CTA only
+__device__ __forceinline__ void umma_f16_2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once the pair's tcgen05 operations issued so far have completed
+__device__ __forceinline__ void umma_commit2(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+// shared::cluster address of `bar` in the leader CTA (rank 0 of the pair): the peer bit of the window is bit 24
+__device__ __forceinline__ uint32_t leader_bar(const uint64_t *bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+// TMA tile load whose completion bytes are credited to the LEADER's mbarrier (both CTAs of the pair issue it)
+__device__ __forceinline__ void tma_tensor2d_g2s_pair(void *dst_smem, const void *tmap, int c0, int c1, const uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(leader_bar(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(const uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_bar(bar)) : "memory");
+}
+
 // one lane of the (converged) warp; the same lane every time, so a commit follows the MMAs of its own thread
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -349,36 +405,48 @@ __device__ __forceinline__ void refine_pad(const FastArgs &args, unsigned int po
 }
 
 // ---- the sweep --------------------------------------------------------------------------------------
+template <bool PAIR>
 __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs args, const __grid_constant__ CUtensorMap tm_q,
                                                                   const __grid_constant__ CUtensorMap tm_e) {
+    using Cfg = FastCfg<PAIR>;
+    using FastSmem = FastSmemT<PAIR>;
+    constexpr int kStages = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader: issues the MMAs, owns the `full` / d_empty barriers
 
     if (tid == 0) {
         mbar_init(&sm.a_full, 1);
         mbar_init(&sm.a_empty, 1);
-        for (int s = 0; s < kFStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&sm.b_full[s], 1);
             mbar_init(&sm.b_empty[s], 1);
         }
         for (int i = 0; i < kFBufs; ++i) {
             mbar_init(&sm.d_full[i], 1);
-            mbar_init(&sm.d_empty[i], kFEpiWarps);   // one arrival per epilogue warp
+            mbar_init(&sm.d_empty[i], (PAIR ? 2 : 1) * kFEpiWarps);   // one arrival per epilogue warp (of both CTAs)
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(&sm.tmem_base, kTmemCols);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc2(&sm.tmem_base, kTmemCols);
+        else tmem_alloc(&sm.tmem_base, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();              // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
     // this CTA's share of the (query block, candidate tile) list, candidates fastest so the query block stays resident
     const long long total = args.m_tiles * args.n_tiles;
-    const long long id_begin = total * blockIdx.x / gridDim.x, id_end = total * (blockIdx.x + 1) / gridDim.x;
-    // 128-query halves of query block m that hold real queries (the last block may have one)
-    auto halves_of = [&](long long m) -> int { return (2 * args.b - m * (kFH * kFM) > kFM) ? 2 : 1; };
+    const long long unit = PAIR ? blockIdx.x >> 1 : blockIdx.x, units = PAIR ? gridDim.x >> 1 : gridDim.x;   // both CTAs of a pair walk the same list
+    const long long id_begin = total * unit / units, id_end = total * (unit + 1) / units;
+    const long long q0_of_cta = (long long)rank * (kFH * kFM);       // this CTA's 256 queries inside the item's query block
+    // 128-query halves of query block m that hold real queries (the last block may have one); a pair always runs both
+    // (its MMAs span the two CTAs; padding rows are zeros and are never counted)
+    auto halves_of = [&](long long m) -> int { return (PAIR || 2 * args.b - m * (kFH * kFM) > kFM) ? 2 : 1; };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -389,38 +457,47 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 const long long m = id / args.n_tiles, n = id % args.n_tiles;
                 if (m != cur_m) {
                     mbar_wait(&sm.a_empty, (a_use & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&sm.a_full, kFH * 2 * 2 * kFBox * 2);
+                    // the leader's barrier collects the bytes of both CTAs' query blocks
+                    if (rank == 0) mbar_arrive_expect_tx(&sm.a_full, (PAIR ? 2 : 1) * kFH * 2 * 2 * kFBox * 2);
 #pragma unroll
                     for (int half = 0; half < kFH; ++half)
 #pragma unroll
                         for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
-                            for (int kb = 0; kb < 2; ++kb)
-                                tma_tensor2d_g2s(&sm.a[half][hl][kb][0], &tm_q, kb * kFKB,
-                                                 (int)(hl * args.q_pad + m * (kFH * kFM) + half * kFM), &sm.a_full);
+                            for (int kb = 0; kb < 2; ++kb) {
+                                const int qrow = (int)(hl * args.q_pad + m * Cfg::kQ + q0_of_cta + half * kFM);
+                                if (PAIR) tma_tensor2d_g2s_pair(&sm.a[half][hl][kb][0], &tm_q, kb * kFKB, qrow, &sm.a_full);
+                                else tma_tensor2d_g2s(&sm.a[half][hl][kb][0], &tm_q, kb * kFKB, qrow, &sm.a_full);
+                            }
                     ++a_use;
                     cur_m = m;
                 }
                 for (int kb = 0; kb < 2; ++kb, ++kbit) {
-                    const int stage = kbit % kFStages;
-                    const uint32_t use = kbit / kFStages;
+                    const int stage = kbit % kStages;
+                    const uint32_t use = kbit / kStages;
                     mbar_wait(&sm.b_empty[stage], (use & 1u) ^ 1u);
-                    if ((args.debug & 2) && kbit >= kFStages) { mbar_arrive(&sm.b_full[stage]); continue; }
-                    mbar_arrive_expect_tx(&sm.b_full[stage], 2 * kFBoxB * 2);
-                    tma_tensor2d_g2s(&sm.b[stage][0][0], &tm_e, kb * kFKB, (int)(n * kFN), &sm.b_full[stage]);
-                    tma_tensor2d_g2s(&sm.b[stage][1][0], &tm_e, kb * kFKB, (int)(args.n_pad + n * kFN), &sm.b_full[stage]);
+                    if (!PAIR && (args.debug & 2) && kbit >= kStages) { mbar_arrive(&sm.b_full[stage]); continue; }
+                    if (rank == 0) mbar_arrive_expect_tx(&sm.b_full[stage], (PAIR ? 2 : 1) * 2 * Cfg::kBoxB * 2);
+                    const int crow = (int)(n * kFN + rank * Cfg::kRowsB);     // a pair splits the 128 candidate rows
+                    if (PAIR) {
+                        tma_tensor2d_g2s_pair(&sm.b[stage][0][0], &tm_e, kb * kFKB, crow, &sm.b_full[stage]);
+                        tma_tensor2d_g2s_pair(&sm.b[stage][1][0], &tm_e, kb * kFKB, (int)args.n_pad + crow, &sm.b_full[stage]);
+                    } else {
+                        tma_tensor2d_g2s(&sm.b[stage][0][0], &tm_e, kb * kFKB, crow, &sm.b_full[stage]);
+                        tma_tensor2d_g2s(&sm.b[stage][1][0], &tm_e, kb * kFKB, (int)args.n_pad + crow, &sm.b_full[stage]);
+                    }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (the leader CTA of a pair) =====================
         // The WHOLE warp runs this loop in convergent code and one elected lane issues the tcgen05 instructions: every
         // operand (descriptors, TMEM addresses) is then provably warp-uniform and lives in uniform registers.  With the
         // loop under `if (lane == 0)` ptxas had to move each operand into a uniform register through an ELECT /
         // R2UR.BROADCAST / BRA.U.ANY waterfall -- 13 dependent instructions in front of every UTCHMMA, 118 clocks per
         // MMA issued against the 64-clock floor of an M128 x N128 x K16 MMA (profiles/r02_fast_kernel_experiments.txt).
-        constexpr uint32_t idesc = umma_idesc_f16(kFM, kFN);
+        constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kFM : kFM, kFN);
         long long cur_m = -1;
         uint32_t a_use = 0, kbit = 0, it = 0;
         int halves = kFH;
@@ -436,8 +513,8 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
             mbar_wait(&sm.d_empty[buf], (duse & 1u) ^ 1u);          // epilogue has drained these accumulators
             tc_fence_after();
             for (int kb = 0; kb < 2; ++kb, ++kbit) {
-                const int stage = kbit % kFStages;
-                const uint32_t use = kbit / kFStages;
+                const int stage = kbit % kStages;
+                const uint32_t use = kbit / kStages;
                 mbar_wait(&sm.b_full[stage], use & 1u);
                 tc_fence_after();
                 const uint64_t b_hi = umma_smem_desc(&sm.b[stage][0][0]), b_lo = umma_smem_desc(&sm.b[stage][1][0]);
@@ -448,19 +525,34 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
 #pragma unroll
                         for (int ks = 0; ks < kFKB / 16; ++ks) {        // 16 halves = 32 bytes = 2 descriptor units per step
                             const uint64_t o = (uint64_t)(ks * 2);
-                            umma_f16(d_tmem, a_lo + o, b_hi + o, idesc, (kb | ks) != 0);
-                            umma_f16(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
-                            umma_f16(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+                            if (PAIR) {
+                                umma_f16_2(d_tmem, a_lo + o, b_hi + o, idesc, (kb | ks) != 0);
+                                umma_f16_2(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+                                umma_f16_2(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, a_lo + o, b_hi + o, idesc, (kb | ks) != 0);
+                                umma_f16(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+                                umma_f16(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+                            }
                         }
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma_commit(&sm.b_empty[stage]);   // frees the stage once these MMAs have read it
+                if (elect_one()) {                                  // frees the stage (in both CTAs) once these MMAs have read it
+                    if (PAIR) umma_commit2(&sm.b_empty[stage]);
+                    else umma_commit(&sm.b_empty[stage]);
+                }
                 __syncwarp();
             }
             if (elect_one()) {
-                umma_commit(&sm.d_full[buf]);
-                if (id + 1 == id_end || (id + 1) / args.n_tiles != m) umma_commit(&sm.a_empty);
+                const bool last_of_block = id + 1 == id_end || (id + 1) / args.n_tiles != m;
+                if (PAIR) {
+                    umma_commit2(&sm.d_full[buf]);
+                    if (last_of_block) umma_commit2(&sm.a_empty);
+                } else {
+                    umma_commit(&sm.d_full[buf]);
+                    if (last_of_block) umma_commit(&sm.a_empty);
+                }
             }
             __syncwarp();
         }
@@ -496,7 +588,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 halves = halves_of(m);
 #pragma unroll
                 for (int h = 0; h < kFH; ++h) {
-                    const long long q = m * (kFH * kFM) + h * kFM + row;
+                    const long long q = m * Cfg::kQ + q0_of_cta + h * kFM + row;
                     valid_q[h] = q < 2 * args.b;
                     if (valid_q[h]) {
                         slot[h] = q < args.b ? q : args.tail_off + (q - args.b);
@@ -522,7 +614,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 const long long self_col = self_local[h] - tile_base;    // column of the true entity, if in this tile
                 const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + buf * (kFH * kFN) + h * kFN;
                 const float st = th[h];
-                const long long q = m * (kFH * kFM) + h * kFM + row;
+                const long long q = m * Cfg::kQ + q0_of_cta + h * kFM + row;
 #pragma unroll 1
                 for (int ch = part; ch < kFN / 32; ch += kFEpiWarps / 4) {
                     uint32_t v[32];
@@ -628,15 +720,22 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.d_empty[buf]);
+            if (lane == 0) {                                             // the leader's MMA warp waits for both CTAs' epilogues
+                if (PAIR) mbar_arrive_leader(&sm.d_empty[buf]);
+                else mbar_arrive(&sm.d_empty[buf]);
+            }
         }
         flush();
         if (args.refine) refine_pad(args, wl_pos, wl_end, lane);
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+    if (PAIR) cluster_sync_all();              // the peer may still be read by the pair's MMAs / signalled by this CTA
+    else __syncthreads();
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc2(tmem, kTmemCols);
+        else tmem_dealloc(tmem, kTmemCols);
+    }
 }
 
 // ---- refine pass: exact verdicts for the band -----------------------------------------------------------
@@ -724,7 +823,7 @@ static long long round_up(long long x, long long m) { return (x + m - 1) / m * m
 long long fast_table_ws_bytes(long long n_local) { return 2 * round_up(n_local > 0 ? n_local : 1, kFN) * kD * 2 + 256; }
 // queries: hi + lo halves of q_pad rows, self ids, scales
 long long fast_query_ws_bytes(long long t) {
-    const long long q_pad = round_up(2 * (t > 0 ? t : 1), kFH * kFM);
+    const long long q_pad = round_up(2 * (t > 0 ? t : 1), 2 * kFH * kFM);      // a CTA pair's query block
     return 2 * q_pad * kD * 2 + q_pad * 8 + q_pad * 4 + q_pad * 4;     // + the refine band per query row
 }
 // worklist of the refine pass: header + capacity (query, candidate) pairs
@@ -777,8 +876,16 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     }
     FastArgs a{};
     a.n_local = n_local; a.ent_offset = ent_offset; a.n_pad = round_up(n_local, kFN);
-    a.b = b; a.tail_off = tail_off; a.q_pad = round_up(2 * b, kFH * kFM);
-    a.m_tiles = a.q_pad / (kFH * kFM); a.n_tiles = a.n_pad / kFN;
+    a.b = b; a.tail_off = tail_off; a.q_pad = round_up(2 * b, 2 * kFH * kFM);
+    // CTA pairs (cta_group::2) from 1,024 queries on: below that the 512-query blocks of a pair leave SMs idle
+    static const int pair_env = []() {
+        const char *e = getenv("BLP_FAST_PAIR");          // experiments: 0 / 1 forces the choice
+        return e ? atoi(e) : -1;
+    }();
+    const long long sms = num_sms_fast();
+    a.pair = (pair_env >= 0 ? pair_env != 0 : 2 * b >= 1024) && sms >= 2 ? 1 : 0;
+    const long long qblock = (a.pair ? 2 : 1) * kFH * kFM;
+    a.m_tiles = a.q_pad / qblock; a.n_tiles = a.n_pad / kFN;
     __half *qsplit = reinterpret_cast<__half *>(query_ws);
     long long *self_id = reinterpret_cast<long long *>(qsplit + 2 * a.q_pad * kD);
     float *qscale = reinterpret_cast<float *>(self_id + a.q_pad);
@@ -816,19 +923,38 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     CUtensorMap tm_q, tm_e;
     memset(&tm_q, 0, sizeof(tm_q));
     memset(&tm_e, 0, sizeof(tm_e));
-    if (!make_rows_tmap(&tm_q, qsplit, 2 * a.q_pad, kFM) || !make_rows_tmap(&tm_e, table_ws, 2 * a.n_pad, kFN)) {
+    if (!make_rows_tmap(&tm_q, qsplit, 2 * a.q_pad, kFM) ||
+        !make_rows_tmap(&tm_e, table_ws, 2 * a.n_pad, a.pair ? kFN / 2 : kFN)) {
         set_error("cuTensorMapEncodeTiled failed for the fast-mode operand tables");
         return BLP_ECUDA;
     }
-    const size_t smem = sizeof(FastSmem) + 1024;
-    BLP_CUDA(cudaFuncSetAttribute(fast_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long items = a.m_tiles * a.n_tiles;
     if (items == 0) return BLP_OK;
-    const long long sms = num_sms_fast();
-    const unsigned grid = (unsigned)(items < sms ? items : sms);
-    prof_begin(1, st);
-    fast_sweep_kernel<<<grid, kFThreads, smem, st>>>(a, tm_q, tm_e);
-    prof_end(1, st);
+    if (a.pair) {
+        const size_t smem = sizeof(FastSmemT<true>) + 1024;
+        BLP_CUDA(cudaFuncSetAttribute(fast_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long pairs = sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * (items < pairs ? items : pairs)));
+        cfg.blockDim = dim3(kFThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        prof_begin(1, st);
+        BLP_CUDA(cudaLaunchKernelEx(&cfg, fast_sweep_kernel<true>, a, tm_q, tm_e));
+        prof_end(1, st);
+    } else {
+        const size_t smem = sizeof(FastSmemT<false>) + 1024;
+        BLP_CUDA(cudaFuncSetAttribute(fast_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)(items < sms ? items : sms);
+        prof_begin(1, st);
+        fast_sweep_kernel<false><<<grid, kFThreads, smem, st>>>(a, tm_q, tm_e);
+        prof_end(1, st);
+    }
     count_launch();
     BLP_CUDA(cudaGetLastError());
     if (refine_ws) {

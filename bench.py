@@ -657,6 +657,12 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
 
     # Wikidata5M training batch (scripts/*wikidata5m*: batch_size = 1024) at K = 512 and the reference's K = 64
     lib = ops.lib()
+    try:
+        # the backward scatter adds one 512-byte gradient row per negative into the (2B, 128) table: the rate of the L2
+        # atomic units, measured with the same access pattern and nothing else (blp_atomic_probe)
+        atomic_gbs, _ = ops.atomic_probe(dev, rows=2048, iters=256)
+    except Exception:
+        atomic_gbs = None
     for b, k in ((1024, 512), (1024, 64), (64, 512)):
         g = torch.Generator().manual_seed(0)
         x = torch.nn.functional.normalize(torch.randn(b, 2, 128, generator=g), dim=-1).to(dev)
@@ -680,11 +686,23 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
         alg = 2 * b * 128 * 4 + b * 128 * 4 + b * 8 + b * k * 16 + 3 * b * 128 * 4
         peak = fp32_peak or 37.2
         floor_us = max(lane / (peak * 1e6), alg / (hbm_peak * 1e3))
+        bound = "fp32_alu" if lane / (peak * 1e6) >= alg / (hbm_peak * 1e3) else "hbm"
+        roof = {"bound": bound, "floor_us": floor_us, "frac": floor_us / us, "algorithmic_bytes": alg, "lane_ops": lane}
+        if atomic_gbs:
+            # every active negative adds one 128-float gradient row (its corrupting entity) to grad_ent: with the margin
+            # loss on random embeddings nearly all B * K negatives are active
+            scatter_bytes = b * k * 128 * 4
+            atomic_us = scatter_bytes / (atomic_gbs * 1e3)
+            roof.update({"l2_atomic_GBps_probe": atomic_gbs, "scatter_bytes": scatter_bytes, "l2_atomic_floor_us": atomic_us,
+                         "l2_atomic_frac": atomic_us / us})
+            if atomic_us > floor_us:
+                roof.update({"bound": "l2_atomic", "floor_us": atomic_us, "frac": atomic_us / us,
+                             "note": "the gradient scatter (one fp32 row reduction per negative) is paced by the L2 atomic units: "
+                                     "floor = scatter bytes / red.global.add.v4.f32 rate measured in this run with the same access "
+                                     "pattern (blp_atomic_probe); fp32_alu / hbm floors kept in lane_ops / algorithmic_bytes"})
         legs[f"train_transe_b{b}_k{k}"] = {
             "config": f"compute_loss forward + backward, BLP-transe dim=128, B={b}, K={k}, margin loss (one fused launch)",
-            "us_per_step_kernels": us, "triples_per_s": b * (k + 1) / (us * 1e-6),
-            "roofline": {"bound": "fp32_alu" if lane / (peak * 1e6) >= alg / (hbm_peak * 1e3) else "hbm", "floor_us": floor_us,
-                         "frac": floor_us / us, "algorithmic_bytes": alg, "lane_ops": lane}}
+            "us_per_step_kernels": us, "triples_per_s": b * (k + 1) / (us * 1e-6), "roofline": roof}
     return legs
 
 

@@ -69,6 +69,7 @@ SYMBOLS = {
     "blp_profile_events": (_i32, [_i32, _vp, _vp]),
     "blp_debug_timestamps": (_i32, [_vp]),
     "blp_pipe_probe": (_i32, [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
+    "blp_atomic_probe": (_i32, [_vp, _i64, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 
 _lib = None

@@ -87,9 +87,40 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(float *sink, int iters,
     sink[(long long)blockIdx.x * blockDim.x + threadIdx.x] = out;
 }
 
+// fp32 reduction (red.global.add.v4.f32) throughput into a small L2-resident table with the access pattern of the
+// gradient scatter of blp_train.cu: a group of 8 lanes adds one whole 128-float row (4 x 16 bytes per lane, 512
+// contiguous bytes per group and instruction round) to a pseudo-random row, nothing else.  Bounds the backward pass of
+// compute_loss at large B x K, which is paced by the L2 atomic units.
+__global__ void __launch_bounds__(512) atomic_probe_kernel(float *table, unsigned int rows, int iters) {
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    unsigned int state = ((blockIdx.x * blockDim.x + threadIdx.x) >> 3) * 2654435761u + 12345u;   // one stream per lane group
+    for (int it = 0; it < iters; ++it) {
+        state = state * 1664525u + 1013904223u;
+        float *row = table + (size_t)((state >> 8) % rows) * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float *p = row + 4 * (gl + 8 * c);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(1.0f), "f"(0.5f), "f"(0.25f), "f"(2.0f) : "memory");
+        }
+    }
+}
+
 }  // namespace blp
 
 using namespace blp;
+
+extern "C" int blp_atomic_probe(float *table, int64_t rows, int iters, double *bytes_host, void *stream) {
+    reset_launch_count();
+    if (!table || rows <= 0 || rows > (1ll << 30) || iters <= 0) { set_error("bad probe arguments"); return BLP_EINVAL; }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned blocks = (unsigned)(sms > 0 ? sms : 148);
+    atomic_probe_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(table, (unsigned int)rows, iters);
+    count_launch();
+    BLP_CUDA(cudaGetLastError());
+    if (bytes_host) *bytes_host = (double)blocks * (512 / 8) * 512.0 * iters;      // groups x 512 bytes per iteration
+    return BLP_OK;
+}
 
 extern "C" int blp_pipe_probe(int variant, float *sink, int64_t n_threads, int iters, double *lane_ops_host,
                               void *stream) {

@@ -743,3 +743,21 @@ def pipe_probe(variant, device, n_threads=148 * 8 * 256, iters=4096):
         _, stream = _enter(dev)
         check(lib().blp_pipe_probe(int(variant), _ptr(sink), n_threads, iters, ctypes.byref(ops), stream), "blp_pipe_probe")
     return ops.value, sink
+
+
+def atomic_probe(device, rows=2048, iters=256):
+    """fp32 reduction throughput into an L2-resident (rows, 128) table (blp_atomic_probe): returns (GB/s, table)."""
+    dev = torch.device(device)
+    table = torch.zeros((rows, 128), dtype=torch.float32, device=dev)
+    nbytes = ctypes.c_double(0.0)
+    with _guard(dev):
+        _, stream = _enter(dev)
+        for _ in range(2):
+            check(lib().blp_atomic_probe(_ptr(table), rows, iters, ctypes.byref(nbytes), stream), "blp_atomic_probe")
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            check(lib().blp_atomic_probe(_ptr(table), rows, iters, ctypes.byref(nbytes), stream), "blp_atomic_probe")
+        b.record()
+        torch.cuda.synchronize(dev)
+    return 5 * nbytes.value / (a.elapsed_time(b) * 1e-3) / 1e9, table

@@ -372,6 +372,10 @@ int blp_store_rows(const float *emb, int64_t m, int d, int normalize, const int6
  * *lane_ops_host receives the number of fp32 lane operations issued (adds and
  * multiplies). */
 int blp_pipe_probe(int variant, float *sink, int64_t n_threads, int iters, double *lane_ops_host, void *stream);
+/* Measurement aid: fp32 reduction (red.global.add.v4.f32) throughput into an L2-resident [rows, 128] table with the
+ * access pattern of the compute_loss gradient scatter (whole 512-byte rows at random): one CTA of 64 lane groups per
+ * SM, `iters` rows per group; *bytes_host receives the bytes added.  The table is modified. */
+int blp_atomic_probe(float *table, int64_t rows, int iters, double *bytes_host, void *stream);
 
 /* Bracket the dominant kernel of the following calls on THIS thread with the
  * caller's CUDA events (cudaEvent_t passed as void*), recorded on the stream the

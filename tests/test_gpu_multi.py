@@ -52,7 +52,8 @@ def _worker(rank, world, port, model, mode, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model,mode", [("transe", "exact"), ("complex", "exact"), ("distmult", "fast")])
+@pytest.mark.parametrize("model,mode", [("transe", "exact"), ("complex", "exact"), ("distmult", "fast"),
+                                        ("complex", "fast_exact"), ("distmult", "fast_exact")])
 def test_nccl_sharded_sweep_equals_single_gpu(model, mode, cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -64,7 +65,7 @@ def test_nccl_sharded_sweep_equals_single_gpu(model, mode, cuda_device):
     single = blp_b200.rank_sweep(model, ent, rel, rows.to(cuda_device), filter_index=didx, mode="exact")
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), model, mode, ret), nprocs=world, join=True)
-    if mode == "exact":
+    if mode in ("exact", "fast_exact"):       # fast_exact: tensor-core sweep + exact refine per shard, the same integers
         for k in ("gt", "ge", "gt_f", "ge_f"):
             assert np.array_equal(ret[k], single[k].cpu().numpy()), k
         want = dict(zip(g["scalar_names"].tolist(), g["scalar_values"].tolist()))

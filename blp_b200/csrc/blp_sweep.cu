@@ -52,8 +52,13 @@ constexpr int kCW = 8;                        // consumer warps (default; Cfg<4,
 constexpr int kCT = 128;                      // candidate rows per tile
 constexpr int kSmemBudget = 227 * 1024 - 1024;
 
-template <int TQP_, int TC_, int CW_ = kCW>
+// TS_ (tile split): every slot ranks the SAME triples and the slots take turns on the candidate tiles (slot = tile index
+// mod NS), instead of every slot ranking its own triples on every tile.  Cfg<2, 1, 8, true> is the pass-size-2 shape
+// (Wikidata5M eval batch): a thread holds the head AND the tail pair of the two triples for one row -- two independent
+// accumulation chains and one candidate load for both -- where Cfg<1, 1> gives a thread a single chain.
+template <int TQP_, int TC_, int CW_ = kCW, bool TS_ = false>
 struct Cfg {
+    static constexpr bool TS = TS_;
     static constexpr int TQP = TQP_;          // query pairs per consumer thread
     static constexpr int TC = TC_;            // candidates per consumer thread
     static constexpr int CW = CW_;            // consumer warps of the CTA
@@ -99,7 +104,11 @@ struct __align__(1024) SweepSmem {
     const float *rowp[C::NQ][3];              // h / t / r row of every query of the current group
     int rowok[C::NQ][3];                      // index inside its table (h / t / r)
     float st[C::NQ];                          // true-triple scores of the current group's queries
-    uint64_t full_bar[ST];
+    // tile split: a parity wait is only sound for a waiter that observes EVERY phase of its barrier, and a slot sees only
+    // every NS-th tile -- so each (slot, buffer) combination gets its own `full` barrier (tile it -> it % (ST * NS)); the
+    // producer is the only waiter of the `empty` barriers and sees all of their phases
+    static constexpr int kFull = ST * (C::TS ? C::NS : 1);
+    uint64_t full_bar[kFull];
     uint64_t empty_bar[ST];
 };
 
@@ -549,14 +558,14 @@ struct QueryMap {
     static constexpr bool kSplit = ROLES == 3 && C::TQP == 1;
     static constexpr int kTriplesPerSlot = kMixed ? C::TQP : C::SQ;
     static constexpr int kRoleSlots = kSplit ? C::NS / 2 : C::NS;
-    static constexpr int kTriplesPerGroup = kRoleSlots * kTriplesPerSlot;
+    static constexpr int kTriplesPerGroup = C::TS ? kTriplesPerSlot : kRoleSlots * kTriplesPerSlot;
     __device__ static __forceinline__ bool is_head(int slot, int qi) {
         if (kMixed) return qi < C::TQP;
         if (kSplit) return slot < C::NS / 2;
         return ROLES == 1;
     }
     __device__ static __forceinline__ int triple(int slot, int qi) {      // offset inside the group
-        if (kMixed) return slot * C::TQP + (qi % C::TQP);
+        if (kMixed) return (C::TS ? 0 : slot * C::TQP) + (qi % C::TQP);
         if (kSplit) return (slot % (C::NS / 2)) * C::SQ + qi;
         return slot * C::SQ + qi;
     }
@@ -573,10 +582,9 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
     BLP_TS(0);
 
     if (tid == 0) {
-        for (int s = 0; s < SM::ST; ++s) {
-            mbar_init(&sm.full_bar[s], 1);
-            mbar_init(&sm.empty_bar[s], C::CW);
-        }
+        for (int s = 0; s < SM::kFull; ++s) mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < SM::ST; ++s)
+            mbar_init(&sm.empty_bar[s], C::TS ? C::CW / C::NS : C::CW);   // tile split: one slot's warps consume a tile
         mbar_fence_init();
     }
     __syncthreads();
@@ -593,6 +601,7 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
             const long long tile = id % ntiles;
             const int buf = it % SM::ST;
             const uint32_t use = (uint32_t)(it / SM::ST);
+            uint64_t *full = &sm.full_bar[it % SM::kFull];
             mbar_wait(&sm.empty_bar[buf], (use & 1u) ^ 1u);
             const long long base = tile * kCT;
             const int rows = (int)min((long long)kCT, args.n_local - base);
@@ -600,10 +609,10 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
             if (MODEL == BLP_MODEL_TRANSE && args.use_tma) {
                 // four tensor copies of [128 rows][32 floats]; rows past the end of the table arrive as zeros
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&sm.full_bar[buf], (uint32_t)(kCT * kD * 4));
+                    mbar_arrive_expect_tx(full, (uint32_t)(kCT * kD * 4));
 #pragma unroll
                     for (int cb = 0; cb < 4; ++cb)
-                        tma_tensor2d_g2s(dst + cb * (kCT * 32), &tmap, cb * 32, (int)base, &sm.full_bar[buf]);
+                        tma_tensor2d_g2s(dst + cb * (kCT * 32), &tmap, cb * 32, (int)base, full);
                 }
             } else {
                 // 16-byte chunks; a warp-wide load covers one 512-byte row
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full_bar[buf]);
+                if (lane == 0) mbar_arrive(full);
             }
         }
         return;
@@ -818,10 +827,10 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
         }
 
         for (; id < seg_end; ++id, ++it) {
+            if (C::TS && (it % C::NS) != slot) continue;      // tile split: the other slot's tile
             const long long tile = id % ntiles;
             const int buf = it % SM::ST;
-            const uint32_t use = (uint32_t)(it / SM::ST);
-            mbar_wait(&sm.full_bar[buf], use & 1u);
+            mbar_wait(&sm.full_bar[it % SM::kFull], (uint32_t)(it / SM::kFull) & 1u);
             if (it == 0) BLP_TS(4);
             float s[C::SQ][C::TC];
             if (any) {                            // warp-uniform: slots past the end of the batch have no queries
@@ -1048,13 +1057,14 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
 static int env_sweep_cfg() {
     static const int v = []() {
         const char *e = getenv("BLP_SWEEP_CFG");       // tuning aid: force one register tile
-        return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
+        return (e && e[0] >= '0' && e[0] <= '6') ? e[0] - '0' : -1;
     }();
     return v;
 }
 
 // Register-tile shape by batch size: the smallest slot that holds the batch without padding queries.
-// a.force_cfg (or BLP_SWEEP_CFG=0..4) forces one: 2 / 4 / 8 / 16 / 32 triples per table pass.
+// a.force_cfg (or BLP_SWEEP_CFG=0..6) forces one: 0..4 = 2 / 4 / 8 / 16 / 32 triples per table pass, 5 / 6 = the
+// tile-split forms of 2 / 4.
 template <int MODEL>
 static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
     if (a.roles == 1) return launch_sweep_cfg<MODEL, Cfg<4, 4>, 1>(a, st);   // single role: full tiles only
@@ -1062,11 +1072,17 @@ static int launch_sweep(const SweepArgs &a, cudaStream_t st) {
     // up to 256 triples the 16-triple groups of Cfg<4,2> give twice as many (group, tile) work items, which evens out
     // the per-CTA shares (E = 64: 44 vs 50 us, E = 256: 110 vs 124 us); beyond that the larger register tile of
     // Cfg<4,4> and its shared-relation path win (E = 1024 in relation order: 0.321 vs 0.390 ms)
-    int cfg = a.b <= 2 ? 0 : a.b <= 4 ? 1 : a.b <= 8 ? 2 : a.b <= 256 ? 3 : 4;
-    if (a.force_cfg >= 0 && a.force_cfg <= 4) cfg = a.force_cfg;
+    // 2 / 4 triples per pass (HBM-bound shapes): the tile-split forms -- every thread holds the head AND tail pairs of
+    // the pass for one row (2 / 4 independent chains, one candidate load for all of them), the two slots of a CTA
+    // alternate on the tiles: 4.8 M rows at pass size 2: 0.409 -> 0.341 ms per pass (7.2 TB/s), pass size 4: 0.575 ->
+    // 0.509 ms (profiles/r02_sweep_warp_variants.txt)
+    int cfg = a.b <= 2 ? 5 : a.b <= 4 ? 6 : a.b <= 8 ? 2 : a.b <= 256 ? 3 : 4;
+    if (a.force_cfg >= 0 && a.force_cfg <= 6) cfg = a.force_cfg;
     else if (env_sweep_cfg() >= 0) cfg = env_sweep_cfg();
     switch (cfg) {
     case 0: return launch_sweep_cfg<MODEL, Cfg<1, 1>, 3>(a, st);             //  2 triples / group (split roles)
+    case 5: return launch_sweep_cfg<MODEL, Cfg<2, 1, kCW, true>, 3>(a, st);   //  2 triples / group (tile split: head + tail pair per thread)
+    case 6: return launch_sweep_cfg<MODEL, Cfg<4, 1, kCW, true>, 3>(a, st);   //  4 triples / group (tile split: 2 head + 2 tail pairs per thread)
     case 1: return launch_sweep_cfg<MODEL, Cfg<2, 1>, 3>(a, st);             //  4
     case 2: return launch_sweep_cfg<MODEL, Cfg<4, 1>, 3>(a, st);             //  8
     case 3: return launch_sweep_cfg<MODEL, Cfg<4, 2>, 3>(a, st);             // 16
@@ -1086,7 +1102,7 @@ int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st) {
 // Cfg index whose group holds `group_triples` triples (the reference's eval batch as a table-pass size), -1 = auto
 int sweep_cfg_for_group(long long group_triples) {
     if (group_triples <= 0) return -1;
-    return group_triples <= 2 ? 0 : group_triples <= 4 ? 1 : group_triples <= 8 ? 2 : group_triples <= 16 ? 3 : 4;
+    return group_triples <= 2 ? 5 : group_triples <= 4 ? 6 : group_triples <= 8 ? 2 : group_triples <= 16 ? 3 : 4;
 }
 
 static thread_local unsigned long long *tl_dbg = nullptr;

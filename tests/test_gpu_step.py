@@ -68,6 +68,25 @@ def test_rank_step_forced_table_pass_size(model, group, cuda_device):
     assert np.array_equal(out["ge"].reshape(-1).cpu().numpy(), co["ge"])
 
 
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("group", (2, 4))
+def test_tile_split_pass_sizes_on_many_tiles(model, group, cuda_device):
+    """Pass sizes 2 / 4 run the tile-split register tiles (both slots of a CTA rank the same triples on alternating candidate
+    tiles, one `full` barrier per (slot, buffer)): many tiles per CTA, a ragged last tile, an odd number of triples, three
+    repetitions (the first version raced on its barrier phases once in a few hundred launches)."""
+    n, b = 60_001, 7
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, b, seed=40 + group)
+    co, _, _ = _oracle(model, ent, rel, heads, tails, rels)
+    triples = torch.stack([heads, tails, rels], 1).to(cuda_device)
+    e, r = ent.to(cuda_device), rel.to(cuda_device)
+    for _ in range(3):
+        out, _, launches = _step(model, e, r, triples, cuda_device, group_triples=group)
+        assert launches == 1
+        assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
+        assert np.array_equal(out["gt"].reshape(-1).cpu().numpy(), co["gt"])
+        assert np.array_equal(out["ge"].reshape(-1).cpu().numpy(), co["ge"])
+
+
 def test_rank_step_long_output_range_uses_separate_metrics(cuda_device):
     """2T > 16384: counters zeroed by memset, metrics by their own launch; same results."""
     n, b = 300, 9000

@@ -453,8 +453,10 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
             // ===================== TMA producer =====================
             long long cur_m = -1;
             uint32_t a_use = 0, kbit = 0;
+            // (query block m, candidate tile n) walk incrementally: a 64-bit division per item and role is ~100 instructions
+            long long m = id_begin / args.n_tiles, n = id_begin % args.n_tiles - 1;
             for (long long id = id_begin; id < id_end; ++id) {
-                const long long m = id / args.n_tiles, n = id % args.n_tiles;
+                if (++n == args.n_tiles) { n = 0; ++m; }
                 if (m != cur_m) {
                     mbar_wait(&sm.a_empty, (a_use & 1u) ^ 1u);
                     // the leader's barrier collects the bytes of both CTAs' query blocks
@@ -501,8 +503,9 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
         long long cur_m = -1;
         uint32_t a_use = 0, kbit = 0, it = 0;
         int halves = kFH;
+        long long m = id_begin / args.n_tiles, n = id_begin % args.n_tiles - 1;
         for (long long id = id_begin; id < id_end; ++id, ++it) {
-            const long long m = id / args.n_tiles;
+            if (++n == args.n_tiles) { n = 0; ++m; }
             if (m != cur_m) {
                 mbar_wait(&sm.a_full, a_use & 1u);
                 ++a_use;
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 __syncwarp();
             }
             if (elect_one()) {
-                const bool last_of_block = id + 1 == id_end || (id + 1) / args.n_tiles != m;
+                const bool last_of_block = id + 1 == id_end || n + 1 == args.n_tiles;
                 if (PAIR) {
                     umma_commit2(&sm.d_full[buf]);
                     if (last_of_block) umma_commit2(&sm.a_empty);
@@ -581,8 +584,10 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                 cgt[h] = cge[h] = 0;
             }
         };
+        long long m = id_begin / args.n_tiles, n = id_begin % args.n_tiles - 1;
+        const bool want_scores = args.scores_out != nullptr, refine = args.refine != nullptr;
         for (long long id = id_begin; id < id_end; ++id, ++it) {
-            const long long m = id / args.n_tiles, n = id % args.n_tiles;
+            if (++n == args.n_tiles) { n = 0; ++m; }
             if (m != cur_m) {
                 flush();
                 halves = halves_of(m);
@@ -611,7 +616,9 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
 #pragma unroll
             for (int h = 0; h < kFH; ++h) {
                 if (h >= halves || (args.debug & 1)) continue;           // uniform over the CTA
-                const long long self_col = self_local[h] - tile_base;    // column of the true entity, if in this tile
+                // column of the true entity if it lives in this tile (else out of range)
+                const long long self_off = self_local[h] - tile_base;
+                const int self_col = (!refine && self_off >= 0 && self_off < nvalid) ? (int)self_off : -1;
                 const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + buf * (kFH * kFN) + h * kFN;
                 const float st = th[h];
                 const long long q = m * Cfg::kQ + q0_of_cta + h * kFM + row;
@@ -621,7 +628,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                     __syncwarp();                                        // the TMEM load is warp-collective
                     tmem_ld32(taddr + ch * 32, v);
                     tmem_ld_wait();
-                    if (args.scores_out && q < 2 * args.b) {
+                    if (want_scores && q < 2 * args.b) {
                         float *orow = args.scores_out + q * args.ld_scores + tile_base + ch * 32;
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
@@ -652,7 +659,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                         }
                         gs = (g[0] + g[1]) + (g[2] + g[3]);
                         es = (e[0] + e[1]) + (e[2] + e[3]);
-                        if (!args.refine && self_col >= ch * 32 && self_col < ch * 32 + 32 && self_col < nvalid) {
+                        if ((self_col >> 5) == ch) {
                             // the true entity itself: it ties with s_true by definition (utils.py:104-105), whatever
                             // the fast arithmetic produced for it
                             const float s_self = __uint_as_float(select32(v, (int)(self_col & 31)));
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fast_sweep_kernel(const FastArgs
                             es += 1 - (s_self >= st);
                         }
                     }
-                    if (args.refine) {                                   // warp-uniform
+                    if (refine) {                                        // warp-uniform
                         // The band of this 32-column chunk goes to the worklist.  Slots are handed out warp-wide: the
                         // warp owns a block of kRefineBlock entries (ONE global atomic per block -- a returning atomic
                         // per entry on a single address serialises the whole chip: 0.33 -> 1.1 ms per 16,384 triples),

@@ -37,6 +37,7 @@ SYMBOLS = {
     "blp_plan_create": (_i32, [ctypes.POINTER(_vp), _i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,
                                ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp]),
     "blp_plan_run": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "blp_plan_set_overlap": (_i32, [_vp, _i32]),
     "blp_plan_destroy": (None, [_vp]),
     "blp_rank_queries": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                                 ctypes.POINTER(_i64), _i32, _vp, _vp, _vp, _vp, _vp]),

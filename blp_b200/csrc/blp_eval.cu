@@ -268,6 +268,7 @@ struct RankJob {
     const long long *triples; const void *fast_table_ws; void *fast_query_ws; float *fast_scores; long long fast_ld;
     void *fast_refine_ws; long long fast_refine_cap;   // filter + refine: exact ranks on the tensor path (NULL = plain fast mode)
     int phases;                                    // bit 0: true scores + counter reset, bit 1: sweep (+ CSR filter correction)
+    int overlap;                                   // fused step only: programmatic dependent launch (blp_plan_set_overlap)
 };
 
 static RankJob make_job(int model, const float *ent, long long n_local, long long ent_offset, int d, const RowRef &h,
@@ -393,6 +394,7 @@ static int rank_step_impl(RankJob j, const StepOut &o, cudaStream_t st) {
         if (epi) {
             unsigned char *ws = reinterpret_cast<unsigned char *>(o.workspace);
             a.fuse_epilogue = 1;
+            a.overlap = j.overlap;
             a.ticket = reinterpret_cast<unsigned int *>(ws);
             a.gt = reinterpret_cast<int *>(ws + 64);
             a.ge = a.gt + out_len;
@@ -560,6 +562,7 @@ struct RankPlan {
     int model; const float *ent; int64_t n_local, ent_offset; int d; const float *rel_weight; int64_t num_rel, t, tail_off;
     int group_triples; int32_t *gt, *ge; float *true_score; int64_t k_values[8]; int nk; float *recip; uint8_t *hits;
     double *sums; void *workspace;
+    int overlap;
 };
 
 extern "C" int blp_plan_create(void **plan_out, int model, const float *ent, int64_t n_local, int64_t ent_offset, int d,
@@ -573,18 +576,39 @@ extern "C" int blp_plan_create(void **plan_out, int model, const float *ent, int
     if (nk < 0 || nk > 8 || (nk > 0 && !k_values_host)) { set_error("bad k_values (nk <= 8)"); return BLP_EINVAL; }
     if (!rel_weight || num_rel <= 0 || tail_off < t) { set_error("bad argument"); return BLP_EINVAL; }
     RankPlan *p = new RankPlan{model, ent, n_local, ent_offset, d, rel_weight, num_rel, t, tail_off, group_triples, gt, ge,
-                               true_score, {0}, nk, recip, hits, sums, workspace};
+                               true_score, {0}, nk, recip, hits, sums, workspace, 0};
     for (int i = 0; i < nk; ++i) p->k_values[i] = k_values_host[i];
     *plan_out = p;
+    return BLP_OK;
+}
+
+extern "C" int blp_plan_set_overlap(void *plan, int on) {
+    if (!plan) { set_error("null plan"); return BLP_EINVAL; }
+    reinterpret_cast<RankPlan *>(plan)->overlap = on ? 1 : 0;
     return BLP_OK;
 }
 
 extern "C" int blp_plan_run(void *plan, const int64_t *triples, const float *h_rows, const float *t_rows, void *stream) {
     if (!plan) { set_error("null plan"); return BLP_EINVAL; }
     const RankPlan *p = reinterpret_cast<const RankPlan *>(plan);
-    return blp_rank_step(p->model, p->ent, p->n_local, p->ent_offset, p->d, p->rel_weight, p->num_rel, triples, p->t, h_rows,
-                         t_rows, p->tail_off, p->group_triples, p->gt, p->ge, p->true_score, p->k_values, p->nk, p->recip,
-                         p->hits, p->sums, p->workspace, stream);
+    if (!p->overlap)
+        return blp_rank_step(p->model, p->ent, p->n_local, p->ent_offset, p->d, p->rel_weight, p->num_rel, triples, p->t, h_rows,
+                             t_rows, p->tail_off, p->group_triples, p->gt, p->ge, p->true_score, p->k_values, p->nk, p->recip,
+                             p->hits, p->sums, p->workspace, stream);
+    // as blp_rank_step, launched with programmatic stream serialization
+    reset_launch_count();
+    int rc = check_rank_args(p->model, p->d, p->t, p->n_local, p->ent, nullptr, nullptr, p->gt, p->ge, nullptr, nullptr, p->true_score);
+    if (rc) return rc;
+    if (p->t == 0) return BLP_OK;
+    if ((rc = check_sweep_args(p->rel_weight, p->num_rel, triples, p->t, h_rows, t_rows, p->tail_off, p->n_local))) return rc;
+    StepOut o{};
+    if ((rc = fill_kvalues(o.kv, p->k_values, p->nk))) return rc;
+    o.recip = p->recip; o.hits = p->hits; o.sums = p->sums; o.workspace = p->workspace;
+    const TripleRows q = triple_rows(p->ent, p->n_local, p->ent_offset, p->rel_weight, p->num_rel, triples, h_rows, t_rows);
+    RankJob j = make_job(p->model, p->ent, p->n_local, p->ent_offset, p->d, q.h, q.t, q.r, p->t, p->tail_off, p->gt, p->ge, p->true_score);
+    j.force_cfg = sweep_cfg_for_group(p->group_triples);
+    j.overlap = 1;
+    return rank_step_impl(j, o, (cudaStream_t)stream);
 }
 
 extern "C" void blp_plan_destroy(void *plan) { delete reinterpret_cast<RankPlan *>(plan); }

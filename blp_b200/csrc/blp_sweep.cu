@@ -539,6 +539,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
         if (args.dbg && tid == 0) args.dbg[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();      \
     } while (0)
 
+// Programmatic dependent launch (blp_plan_set_overlap): the next launch of the stream may start while this grid is
+// still running (its CTAs take the SMs as ours exit) and blocks in griddep_wait() until this grid has completed and
+// flushed.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int CW>
 __device__ __forceinline__ void consumer_bar_sync_n() {
     asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
@@ -589,10 +595,21 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
     }
     __syncthreads();
 
+    griddep_launch_dependents();
+    // everything this grid shares with the previous launch of the stream -- the counter workspace, the ticket, the output
+    // arrays -- is touched only after griddep_wait(); in the fused step that is the end of a CTA's first segment, so its
+    // prologue and scoring overlap the tail of the previous batch.  Inputs that a previous KERNEL may have produced
+    // (precomputed true scores) and direct score output wait up front.
+    if (!args.fuse_true || args.scores_out) griddep_wait();
+
     // ---- this CTA's share of the (group, tile) list ---------------------------------------------
     const long long ntiles = (args.n_local + kCT - 1) / kCT;
     const long long total = ntiles * args.groups;
-    const long long id_begin = total * blockIdx.x / gridDim.x, id_end = total * (blockIdx.x + 1) / gridDim.x;
+    // contiguous shares, the CTAs with one item more FIRST: CTAs are dispatched in blockIdx order, so with overlapping
+    // launches (blp_plan_set_overlap) the last-started CTA of a batch -- the one that decides when the batch completes --
+    // is a short one (with the rounding total * b / grid the last CTA always got the long share: no gain from overlap)
+    const long long share = total / gridDim.x, extra = total % gridDim.x, bid = blockIdx.x;
+    const long long id_begin = bid * share + (bid < extra ? bid : extra), id_end = id_begin + share + (bid < extra ? 1 : 0);
 
     if (warp == C::CW) {
         // ===================== producer warp =====================
@@ -663,6 +680,7 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
         const long long grp = id / ntiles;
         const long long seg_end = min(id_end, (grp + 1) * ntiles);
         const long long t0 = grp * QM::kTriplesPerGroup;                   // first triple of this group
+        const bool seg_first = id == grp * ntiles;                         // this CTA owns the group's first tile: it reports the true scores
 
         consumer_bar_sync();                      // everyone is done with the previous group's vectors
         // (1) the h / t / r row of every query of this group, resolved once (one round of index loads)
@@ -771,9 +789,7 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
                     // an index outside the table (train.py:137-138 asserts this never happens): NaN compares false
                     // against every candidate, so the query reports gt = ge = 0 and is detectable
                     const float v = (sm.rowok[ql][0] & sm.rowok[ql][1] & sm.rowok[ql][2]) ? sv : __int_as_float(0x7fc00000);
-                    sm.st[ql] = tr < args.b ? v : 0.0f;
-                    if (tr < args.b && id == grp * ntiles && args.true_score_out)
-                        args.true_score_out[(QM::is_head(s_, qi) ? 0 : tail_base) + tr] = v;
+                    sm.st[ql] = tr < args.b ? v : 0.0f;             // written to true_score_out at the end of the segment
                 }
             }
             __syncwarp();
@@ -883,6 +899,12 @@ __global__ void __launch_bounds__((C::CW + 1) * 32, 1) sweep_kernel(const SweepA
                     }
                 }
             }
+        }
+        griddep_wait();                           // the previous launch of the stream is complete: outputs / workspace are ours
+        if (args.fuse_true && seg_first && args.true_score_out && tid < C::NQ) {
+            const int s_ = tid / C::SQ, qi = tid % C::SQ;
+            const long long tr = t0 + QM::triple(s_, qi);
+            if (tr < args.b) args.true_score_out[(QM::is_head(s_, qi) ? 0 : tail_base) + tr] = sm.st[tid];
         }
         if (!args.scores_out) {
 #pragma unroll
@@ -1047,7 +1069,21 @@ static int launch_sweep_cfg(const SweepArgs &a, cudaStream_t st) {
     }
     if (!(MODEL == BLP_MODEL_TRANSE && args.use_tma)) memset(&tmap, 0, sizeof(tmap));
     prof_begin(1, st);
-    sweep_kernel<MODEL, C, ROLES><<<grid, (C::CW + 1) * 32, smem, st>>>(args, tmap);
+    if (args.overlap) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3((C::CW + 1) * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        BLP_CUDA(cudaLaunchKernelEx(&cfg, sweep_kernel<MODEL, C, ROLES>, args, tmap));
+    } else {
+        sweep_kernel<MODEL, C, ROLES><<<grid, (C::CW + 1) * 32, smem, st>>>(args, tmap);
+    }
     prof_end(1, st);
     count_launch();
     BLP_CUDA(cudaGetLastError());

@@ -213,6 +213,7 @@ struct SweepArgs {
     double *sums;            // optional [1 + nk], train.py:154-157
     long long out_len;       // tail_off + b: length of the output / accumulator index space
     unsigned long long *dbg; // measurement aid (blp_debug_timestamps): 16 globaltimer slots per CTA, or NULL
+    int overlap;             // launch with programmatic stream serialization (blp_plan_set_overlap)
 };
 
 int launch_sweep_dyn(int model, const SweepArgs &a, cudaStream_t st);

@@ -357,7 +357,8 @@ class RankSweepPlan:
     Everything that does not depend on the triples is done once: argument validation, output / scratch
     allocation, and -- exact mode -- the C-side plan object (blp_plan_create) that holds every static argument, so a
     call is ONE ctypes call with three arguments and ONE kernel launch (blp_plan_run: true scores, sweep and metrics
-    fused).  That matters for the reference's small eval batches (64 triples, train.py:128), where host time and
+    fused).  `overlap_calls=True` (exact mode, one GPU, no filter index) lets batch n + 1 start on the SMs batch n has
+    already left -- see blp_plan_set_overlap in include/blp_b200.h for the contract on the inputs.  That matters for the reference's small eval batches (64 triples, train.py:128), where host time and
     launch count are the cost.  With a filter index the correction and the two metric reductions are separate
     launches; the tensor-core mode keeps its fold + sweep + metrics launches.  The returned tensors are STATIC: the
     next call overwrites them.
@@ -367,7 +368,7 @@ class RankSweepPlan:
     """
 
     def __init__(self, rel_model, ent_emb, rel_weight, num_triples, *, mode="exact", filter_index=None,
-                 k_values=K_VALUES, ent_offset=0, group=None, fast_table=None, group_triples=0):
+                 k_values=K_VALUES, ent_offset=0, group=None, fast_table=None, group_triples=0, overlap_calls=False):
         lib = ops.lib()
         self.model_id = ops.model_id(rel_model)
         dev = ops._require_cuda(ent_emb, rel_weight)
@@ -427,6 +428,12 @@ class RankSweepPlan:
                                           p(o["hits"]) if fm else None, p(o["sums"]) if fm else None, p(self._ws)),
                       "blp_plan_create")
             self._plan = handle
+            if overlap_calls:
+                # consecutive calls overlap on the GPU (programmatic dependent launch, blp_plan_set_overlap).  CONTRACT: the
+                # table, the relation table and every `triples` / h_rows / t_rows passed to a call are complete when the call
+                # is enqueued (resident tensors and their slices, host copies) -- not the output of a kernel enqueued just
+                # before it on the same stream
+                ops.check(lib.blp_plan_set_overlap(handle, 1), "blp_plan_set_overlap")
         # blp_rank_sweep_fast(model, ent, n, off, d, rel, R, TRIPLES, t, H_ROWS, T_ROWS, indptr, idx, tail_off, gt, ge, gt_f, ge_f, ts, ...)
         self._head = (self.model_id, p(ent_emb), n, self.ent_offset, d, p(self.rel), self.rel.shape[0])
         self._tail = (None, None, T, p(o["gt"]), p(o["ge"]), None, None, p(o["true_score"]))

@@ -161,3 +161,38 @@ def test_plan_one_launch_per_batch(model, cuda_device):
         assert np.array_equal(out["true_score"].reshape(-1).cpu().numpy(), co["true_score"])
         assert np.array_equal(out["recip"].cpu().numpy().reshape(-1), recip.reshape(-1))
         assert abs(float(out["sums"][0]) - recip.astype(np.float64).sum()) < 1e-9
+
+
+@pytest.mark.parametrize("model", ("transe", "distmult"))
+def test_plan_overlapping_calls_equal_serial_calls(model, cuda_device):
+    """RankSweepPlan(overlap_calls=True): batch n + 1 is launched with programmatic stream serialization and starts while
+    batch n is still finishing; it must not touch the shared workspace / outputs before batch n is complete.  Every
+    batch of a back-to-back sequence must give the serial plan's numbers (checked through asynchronous copies between
+    the calls, and -- pure kernel-after-kernel -- through the state the sequence leaves behind)."""
+    n, e, n_batches = 14541, 64, 6
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, e * n_batches, seed=91, n_rel=37)
+    dev = cuda_device
+    en, rl = ent.to(dev), rel.to(dev)
+    triples = torch.stack([heads, tails, rels], 1).to(dev)
+    batches = [triples[i * e:(i + 1) * e] for i in range(n_batches)]          # slices of a resident tensor
+    serial = blp_b200.RankSweepPlan(model, en, rl, e)
+    want = []
+    for bt in batches:
+        o = serial(bt)
+        want.append({k: o[k].clone() for k in ("gt", "ge", "true_score", "sums")})
+    torch.cuda.synchronize()
+    plan = blp_b200.RankSweepPlan(model, en, rl, e, overlap_calls=True)
+    got = []
+    for bt in batches:                                 # copies between the calls
+        o = plan(bt)
+        got.append({k: o[k].clone() for k in ("gt", "ge", "true_score", "sums")})
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        for k in w:
+            assert torch.equal(w[k], g[k]), k
+    for rep in range(40):                              # kernel directly after kernel
+        o = plan(batches[rep % n_batches])
+    o = plan(batches[2])
+    torch.cuda.synchronize()
+    for k in want[2]:
+        assert torch.equal(want[2][k], o[k]), k

@@ -27,7 +27,7 @@ triples = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, 
 if os.environ.get("SORT_REL"):
     triples = triples[torch.argsort(triples[:, 2], stable=True)]
 triples = triples.contiguous().to(dev)
-plan = blp_b200.RankSweepPlan(model, ent, rel, E, group_triples=group)
+plan = blp_b200.RankSweepPlan(model, ent, rel, E, group_triples=group, overlap_calls=bool(os.environ.get("OVERLAP")))
 for _ in range(5):
     out = plan(triples)
 torch.cuda.synchronize()

@@ -560,7 +560,7 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
     legs = {}
     sums_of = {}
 
-    def sweep_leg(name, dataset, model, mode, e):
+    def sweep_leg(name, dataset, model, mode, e, overlap=False):
         w = make_workload(args, dataset, model)
         ent, rel = w["ent"].to(dev), w["rel"].to(dev)
         tr = w["triples"][torch.argsort(w["triples"][:, 2], stable=True)].contiguous()
@@ -579,7 +579,7 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
         else:
             chunks = [tr[torch.arange(c * e, (c + 1) * e) % w["t"]].contiguous().to(dev) for c in range(max(1, w["t"] // e))]
             ft = ops.fast_table(ent) if mode.startswith("fast") else None
-            plan = blp_b200.RankSweepPlan(model, ent, rel, e, mode=mode, fast_table=ft)
+            plan = blp_b200.RankSweepPlan(model, ent, rel, e, mode=mode, fast_table=ft, overlap_calls=overlap)
 
             def call():
                 out = plan(chunks[state["i"] % len(chunks)])
@@ -621,6 +621,9 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
             leg["refine_overflow"] = bool(int(st[1]))
             leg["note"] = ("tensor-core sweep + exact re-scoring of the candidates inside the a-priori error band around the true "
                            "score: integer ranks bit-identical to the exact mode (DESIGN 4.2b)")
+        if overlap:
+            leg["note"] = ("consecutive calls launched with programmatic stream serialization (RankSweepPlan(overlap_calls=True), "
+                           "blp_plan_set_overlap): batch n + 1 starts on the SMs batch n has left; every chunk is a resident tensor")
         legs[name] = leg
 
     # one call per evaluation set, like the headline step (FB15k-237: 20,480 test triples, WN18RR: 3,136)
@@ -637,6 +640,7 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
         legs[ds_model + "_fast_exact"]["metrics_equal_exact_leg"] = bool(
             torch.equal(a_[1:], b_[1:]) and abs(float(a_[0]) - float(b_[0])) <= 1e-12 * abs(float(a_[0])))
     sweep_leg("fb15k237_transe_eval_batch_64", "fb15k237", "transe", "exact", 64)     # the reference's eval_batch_size
+    sweep_leg("fb15k237_transe_eval_batch_64_overlapped", "fb15k237", "transe", "exact", 64, overlap=True)
 
     # BOW script widths (TransE, D = 300 glove-bow / 768 bert-bow, scripts/test-umls.sh): the D != 128 path
     for d_bow, name in ((300, "fb15k237_transe_d300"), (768, "fb15k237_transe_d768")):
@@ -1019,7 +1023,8 @@ def main_b200(args):
         for nm, tag in (("fb15k237_distmult_fast", "distmult_fast"), ("fb15k237_distmult_exact", "distmult_exact"),
                         ("fb15k237_distmult_fast_exact", "distmult_fast_exact"), ("wn18rr_complex_fast_exact", "complex_fast_exact"),
                         ("wn18rr_complex_fast", "complex_fast"), ("wn18rr_complex_exact", "complex_exact"),
-                        ("fb15k237_transe_eval_batch_64", "transe_e64"), ("fb15k237_transe_d768", "transe_d768"),
+                        ("fb15k237_transe_eval_batch_64", "transe_e64"), ("fb15k237_transe_eval_batch_64_overlapped", "transe_e64_overlapped"),
+                        ("fb15k237_transe_d768", "transe_d768"),
                         ("train_transe_b1024_k512", "train_b1024")):
             r = legs.get(nm, {}).get("roofline")
             if r:

@@ -298,41 +298,50 @@ __global__ void split_table_kernel(const float4 *__restrict__ ent, long long n_l
 }
 
 // Coefficient of candidate element j for query (triple i, role): the score with the candidate factored out.
+// Value form: xk = x[k], xLk = x[L + k] with k = j mod L, `first` = j < L (DistMult: xk = x[j], the rest unused).
+template <int MODEL>
+__device__ __forceinline__ float fold_coeff_v(bool head_pred, bool first, float hk, float hLk, float tk, float tLk, float rk,
+                                              float rLk) {
+    if (MODEL == BLP_MODEL_DISTMULT) return head_pred ? fmul(rk, tk) : fmul(hk, rk);   // models.py:227
+    if (MODEL == BLP_MODEL_COMPLEX) {   // models.py:230-239; r = (rr | ri), h = (hr | hi), t = (tr | ti)
+        const float rr = rk, ri = rLk;
+        if (head_pred) {                // candidate = h:  hr (rr tr + ri ti) + hi (rr ti - ri tr)
+            const float tr = tk, ti = tLk;
+            return first ? fadd(fmul(rr, tr), fmul(ri, ti)) : fsub(fmul(rr, ti), fmul(ri, tr));
+        }
+        const float hr = hk, hi = hLk;   // candidate = t:  tr (rr hr - ri hi) + ti (rr hi + ri hr)
+        return first ? fsub(fmul(rr, hr), fmul(ri, hi)) : fadd(fmul(rr, hi), fmul(ri, hr));
+    }
+    // SIMPLE, models.py:242-248: 1/2 (hh ra tt + th rb ht); h = (hh | ht), t = (th | tt), r = (ra | rb)
+    if (head_pred) return first ? fmul(0.5f, fmul(rk, tLk)) : fmul(0.5f, fmul(tk, rLk));
+    return first ? fmul(0.5f, fmul(rLk, hLk)) : fmul(0.5f, fmul(hk, rk));
+}
 template <int MODEL>
 __device__ __forceinline__ float fold_coeff(bool head_pred, const float *__restrict__ h, const float *__restrict__ t,
                                             const float *__restrict__ r, int j) {
     constexpr int L = kD / 2;
-    if (MODEL == BLP_MODEL_DISTMULT) return head_pred ? fmul(r[j], t[j]) : fmul(h[j], r[j]);   // models.py:227
+    if (MODEL == BLP_MODEL_DISTMULT) return fold_coeff_v<MODEL>(head_pred, true, h[j], 0.f, t[j], 0.f, r[j], 0.f);
     const int k = j & (L - 1);
-    const bool first = j < L;
-    if (MODEL == BLP_MODEL_COMPLEX) {   // models.py:230-239; r = (rr | ri), h = (hr | hi), t = (tr | ti)
-        const float rr = r[k], ri = r[L + k];
-        if (head_pred) {                // candidate = h:  hr (rr tr + ri ti) + hi (rr ti - ri tr)
-            const float tr = t[k], ti = t[L + k];
-            return first ? fadd(fmul(rr, tr), fmul(ri, ti)) : fsub(fmul(rr, ti), fmul(ri, tr));
-        }
-        const float hr = h[k], hi = h[L + k];   // candidate = t:  tr (rr hr - ri hi) + ti (rr hi + ri hr)
-        return first ? fsub(fmul(rr, hr), fmul(ri, hi)) : fadd(fmul(rr, hi), fmul(ri, hr));
-    }
-    // SIMPLE, models.py:242-248: 1/2 (hh ra tt + th rb ht); h = (hh | ht), t = (th | tt), r = (ra | rb)
-    if (head_pred) return first ? fmul(0.5f, fmul(r[k], t[L + k])) : fmul(0.5f, fmul(t[k], r[L + k]));
-    return first ? fmul(0.5f, fmul(r[L + k], h[L + k])) : fmul(0.5f, fmul(h[k], r[k]));
+    return fold_coeff_v<MODEL>(head_pred, j < L, h[k], h[L + k], t[k], t[L + k], r[k], r[L + k]);
 }
 
 // sum_j fold_abs(j) * |e[j]| bounds the sum of |terms| the reference adds up for candidate e: the magnitude the
 // a-priori error bound of the refine band is relative to (ComplEx folds two products into one coefficient, which may
 // cancel; everything else is a single product, so the bound is |coefficient|).
 template <int MODEL>
+__device__ __forceinline__ float fold_abs_v(bool first, float xk, float xLk, float rk, float rLk, float c) {
+    if (MODEL != BLP_MODEL_COMPLEX) return fabsf(c);
+    const float rr = fabsf(rk), ri = fabsf(rLk), xr = fabsf(xk), xi = fabsf(xLk);   // x = t (head prediction) or h
+    return first ? rr * xr + ri * xi : rr * xi + ri * xr;
+}
+template <int MODEL>
 __device__ __forceinline__ float fold_abs(bool head_pred, const float *__restrict__ h, const float *__restrict__ t,
                                           const float *__restrict__ r, int j, float c) {
     if (MODEL != BLP_MODEL_COMPLEX) return fabsf(c);
     constexpr int L = kD / 2;
     const int k = j & (L - 1);
-    const bool first = j < L;
-    const float rr = fabsf(r[k]), ri = fabsf(r[L + k]);
     const float *x = head_pred ? t : h;
-    const float xr = fabsf(x[k]), xi = fabsf(x[L + k]);
-    return first ? rr * xr + ri * xi : rr * xi + ri * xr;
+    return fold_abs_v<MODEL>(j < L, x[k], x[L + k], r[k], r[L + k], c);
 }
 
 // One CTA of 128 threads per query row: rows [0, b) predict heads, [b, 2b) predict tails, the rest is padding.
@@ -394,6 +403,104 @@ __global__ void __launch_bounds__(kD) fold_queries_kernel(const RowRef hr, const
         // candidate (Cauchy-Schwarz); 1.001 covers the fp32 roundings of the norm itself
         const float cn = sqrtf((s_sq[0] + s_sq[1]) + (s_sq[2] + s_sq[3])) * 1.001f;
         band[q] = kappa * (cn * sq) * (__uint_as_float(table_hdr->max_norm_bits) * table_hdr->scale);
+    }
+}
+
+// The same folding with one WARP per triple (rows 16-byte aligned): the h / t / r rows are read once for both
+// queries of the triple (one float4 per lane and row; the halves models fetch the partner half by shuffle), the row
+// maximum and the band norm are warp reductions (no CTA barrier), hi / lo go out as 8-byte stores.  Per element the
+// operations are fold_coeff_v / split_f16 as above, so the operands are bit-identical to fold_queries_kernel's.
+// Jobs [0, b) are triples; jobs [b, b + q_pad - 2b) are the zero padding rows of the query table.
+constexpr int kFoldWarps = 8;
+__device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                       __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ void emit_folded_row(const float (&c)[4], const float (&ca)[4], long long q, long long self,
+                                                long long q_pad, __half *__restrict__ qsplit, long long *__restrict__ self_id,
+                                                float *__restrict__ qscale, float *__restrict__ band, float kappa,
+                                                float table_scale, float table_norm, int lane) {
+    float m = fmaxf(fmaxf(fabsf(c[0]), fabsf(c[1])), fmaxf(fabsf(c[2]), fabsf(c[3])));
+    float n2 = (ca[0] * ca[0] + ca[1] * ca[1]) + (ca[2] * ca[2] + ca[3] * ca[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    const float sq = pow2_scale(m);
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) split_f16(c[u], sq, hi[u], lo[u]);
+    uint2 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+    reinterpret_cast<uint2 *>(qsplit + q * kD)[lane] = ph;
+    reinterpret_cast<uint2 *>(qsplit + (q_pad + q) * kD)[lane] = pl;
+    if (lane == 0) {
+        self_id[q] = self;
+        qscale[q] = fmul(sq, table_scale);
+        // refine band as in fold_queries_kernel (Cauchy-Schwarz bound; 1.001 covers the fp32 roundings of the norm)
+        band[q] = kappa * ((sqrtf(n2) * 1.001f) * sq) * table_norm;
+    }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kFoldWarps * 32) fold_triples_kernel(const RowRef hr, const RowRef tr, const RowRef rr,
+                                                                       const long long *__restrict__ triples, long long b,
+                                                                       long long q_pad, __half *__restrict__ qsplit,
+                                                                       long long *__restrict__ self_id, float *__restrict__ qscale,
+                                                                       const FastTableHeader *__restrict__ table_hdr,
+                                                                       long long tail_off, float *__restrict__ true_score,
+                                                                       int *__restrict__ gt, int *__restrict__ ge,
+                                                                       float *__restrict__ band, float kappa) {
+    __shared__ __align__(16) float s_terms[kFoldWarps][kD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long job = (long long)blockIdx.x * kFoldWarps + warp;
+    if (job >= b + (q_pad - 2 * b)) return;
+    const float table_scale = table_hdr->scale, table_norm = __uint_as_float(table_hdr->max_norm_bits) * table_scale;
+    if (job >= b) {                                   // padding row of the query table: zeros
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        emit_folded_row(z, z, 2 * b + (job - b), -1, q_pad, qsplit, self_id, qscale, band, kappa, table_scale, table_norm, lane);
+        return;
+    }
+    const long long i = job;
+    const float *h = hr.row(i, kD), *t = tr.row(i, kD), *r = rr.row(i, kD);
+    const float4 hv = __ldg(reinterpret_cast<const float4 *>(h) + lane), tv = __ldg(reinterpret_cast<const float4 *>(t) + lane),
+                 rv = __ldg(reinterpret_cast<const float4 *>(r) + lane);
+    const long long self_h = triples[i * 3 + 0], self_t = triples[i * 3 + 1];
+    constexpr bool kHalves = MODEL != BLP_MODEL_DISTMULT;
+    const bool first = !kHalves || lane < 16;          // this lane's four positions lie in [0, L)
+    float4 hp = hv, tp = tv, rp = rv;                  // the same positions of the other half (halves models)
+    if (kHalves) { hp = shfl_xor4(hv, 16); tp = shfl_xor4(tv, 16); rp = shfl_xor4(rv, 16); }
+    const float ho[4] = {hv.x, hv.y, hv.z, hv.w}, to[4] = {tv.x, tv.y, tv.z, tv.w}, ro[4] = {rv.x, rv.y, rv.z, rv.w};
+    const float hq[4] = {hp.x, hp.y, hp.z, hp.w}, tq[4] = {tp.x, tp.y, tp.z, tp.w}, rq[4] = {rp.x, rp.y, rp.z, rp.w};
+#pragma unroll
+    for (int role = 0; role < 2; ++role) {
+        const bool head_pred = role == 0;
+        float c[4], ca[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // x[k] / x[L + k]: own / partner value in the first half, partner / own in the second
+            const float hk = first ? ho[u] : hq[u], hLk = first ? hq[u] : ho[u];
+            const float tk = first ? to[u] : tq[u], tLk = first ? tq[u] : to[u];
+            const float rk = first ? ro[u] : rq[u], rLk = first ? rq[u] : ro[u];
+            c[u] = fold_coeff_v<MODEL>(head_pred, first, hk, hLk, tk, tLk, rk, rLk);
+            ca[u] = fold_abs_v<MODEL>(first, head_pred ? tk : hk, head_pred ? tLk : hLk, rk, rLk, c[u]);
+        }
+        emit_folded_row(c, ca, head_pred ? i : b + i, head_pred ? self_h : self_t, q_pad, qsplit, self_id, qscale, band, kappa,
+                        table_scale, table_norm, lane);
+    }
+    if (true_score) {
+        float s = true_score_warp128<MODEL>(h, t, r, s_terms[warp], lane);
+        if (lane == 0) {
+            if (!(hr.in_range(i) && tr.in_range(i) && rr.in_range(i))) s = __int_as_float(0x7fc00000);
+            true_score[i] = s;
+            true_score[tail_off + i] = s;
+            gt[i] = 0; gt[tail_off + i] = 0;
+            ge[i] = 0; ge[tail_off + i] = 0;
+        }
     }
 }
 
@@ -919,11 +1026,24 @@ int launch_fast_sweep(int model, long long n_local, long long ent_offset, const 
     }
 
     float *ts_out = compute_true ? true_score : nullptr;
+    // one warp per triple when the rows allow 16-byte loads (every d = 128 table / dense row block that is 16-byte aligned)
+    const bool warp_fold = ((reinterpret_cast<uintptr_t>(h.base) | reinterpret_cast<uintptr_t>(t.base) | reinterpret_cast<uintptr_t>(r.base)) & 15u) == 0;
+    const unsigned fold_grid = (unsigned)((b + (a.q_pad - 2 * b) + kFoldWarps - 1) / kFoldWarps);
+#define BLP_FOLD(M)                                                                                                            \
+    do {                                                                                                                       \
+        if (warp_fold)                                                                                                         \
+            fold_triples_kernel<M><<<fold_grid, kFoldWarps * 32, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, \
+                                                                          tail_off, ts_out, gt, ge, band, kappa);            \
+        else                                                                                                                   \
+            fold_queries_kernel<M><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr,  \
+                                                                     tail_off, ts_out, gt, ge, band, kappa);                 \
+    } while (0)
     switch (model) {
-    case BLP_MODEL_DISTMULT: fold_queries_kernel<BLP_MODEL_DISTMULT><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
-    case BLP_MODEL_COMPLEX: fold_queries_kernel<BLP_MODEL_COMPLEX><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
-    default: fold_queries_kernel<BLP_MODEL_SIMPLE><<<(unsigned)a.q_pad, kD, 0, st>>>(h, t, r, triples, b, a.q_pad, qsplit, self_id, qscale, hdr, tail_off, ts_out, gt, ge, band, kappa); break;
+    case BLP_MODEL_DISTMULT: BLP_FOLD(BLP_MODEL_DISTMULT); break;
+    case BLP_MODEL_COMPLEX: BLP_FOLD(BLP_MODEL_COMPLEX); break;
+    default: BLP_FOLD(BLP_MODEL_SIMPLE); break;
     }
+#undef BLP_FOLD
     count_launch();
     BLP_CUDA(cudaGetLastError());
 

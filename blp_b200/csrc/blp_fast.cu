@@ -210,8 +210,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
 // power-of-two scale that maps max_abs to at most 2^14 (1 when the operand is all zeros / not finite)
 __device__ __forceinline__ float pow2_scale(float max_abs) {
     if (!(max_abs > 0.0f) || !(max_abs < 3.0e38f)) return 1.0f;
+    // max_abs = m * 2^e, m in [0.5, 1): for normal numbers whose scale is a normal number too, e and 2^(target - e) come
+    // straight from the exponent field (frexpf / ldexpf are ~100 instructions each and ran in every lane of the fold)
+    const unsigned int ef = __float_as_uint(max_abs) >> 23;               // sign bit is 0 here
+    if (ef >= 14u && ef <= 254u) return __uint_as_float((267u + (unsigned int)((int)kFTargetExp - 14) - ef) << 23);   // e = ef - 126
     int e;
-    frexpf(max_abs, &e);                                  // max_abs = m * 2^e, m in [0.5, 1)
+    frexpf(max_abs, &e);
     return ldexpf(1.0f, (int)kFTargetExp - e);
 }
 // s*x = hi + lo, both fp16 (round to nearest even); s is a power of two, so s*x is exact

@@ -207,3 +207,24 @@ def test_aligned_triples_sweep_is_bit_identical(model, n_rel, cuda_device):
     lo = blp_b200.rank_sweep(model, e[:1000].contiguous(), r, aligned, h_rows=h_rows, t_rows=t_rows)
     hi = blp_b200.rank_sweep(model, e[1000:].contiguous(), r, aligned, ent_offset=1000, h_rows=h_rows, t_rows=t_rows)
     assert torch.equal(lo["gt"] + hi["gt"], b["gt"]) and torch.equal(lo["ge"] + hi["ge"], b["ge"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("q,k_values", [(40960, [1, 3, 10]), (40963, [1, 3, 10]), (8192, [1, 3, 10, 100]), (40961, [1, 10]),
+                                       (4095, [1, 3, 10])])
+def test_metrics_of_a_whole_evaluation_set(q, k_values, cuda_device):
+    """utils.py:106-109 + train.py:154-157 over a whole evaluation set in one launch (blp_rank_metrics): from 4,096
+    queries on the kernel takes four queries per thread with 16-byte accesses and packed hit bytes (3 or 4 hit
+    positions); reciprocal ranks, hits and the hit counts must equal the oracle's bit for bit, the MRR sum to 1e-12."""
+    g = torch.Generator().manual_seed(q)
+    gt = torch.randint(0, 14541, (q,), generator=g, dtype=torch.int32)
+    gt[::7] = 0                                               # rank-1 queries: hits at every k
+    ge = gt + torch.randint(1, 5, (q,), generator=g, dtype=torch.int32)
+    recip, hits, sums = ops.rank_metrics(gt.to(cuda_device), ge.to(cuda_device), k_values)
+    want_recip, want_hits = c_oracle.metrics_from_counts(gt.numpy(), ge.numpy(), k_values)
+    assert np.array_equal(recip.cpu().numpy(), want_recip)
+    assert np.array_equal(hits.cpu().numpy().astype(np.uint8), want_hits.astype(np.uint8))
+    s = sums.cpu().numpy()
+    assert np.array_equal(s[1:], want_hits.astype(np.float64).sum(0))
+    ref = want_recip.astype(np.float64).sum()
+    assert abs(s[0] - ref) <= 1e-12 * ref

@@ -21,7 +21,7 @@ from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPr
                      complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,
                      margin_loss, nll_loss, simple_score, transe_score)
 from .utils import (DeviceFilterIndex, TripleFilterIndex, get_metrics, get_negative_sampling_indices,  # noqa: F401
-                    graph_edges, make_ent2idx)  # noqa: F401
+                    graph_edges, make_ent2idx, split_by_category, split_by_new_position)  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -32,7 +32,8 @@ def patch(models_module, utils_module=None, lazy_scores=True):
     After `import models, utils; blp_b200.patch(models, utils)` every reference model class
     (BertEmbeddingsLP, BOW, DKRL, ...) built afterwards binds the CUDA score / loss functions
     (models.py:16-24, 31-34), `compute_loss` is the fused kernel, and train.py's
-    `utils.get_metrics(...)` calls run on the GPU.  train.py itself is untouched.
+    `utils.get_metrics(...)` / `utils.split_by_new_position` / `utils.split_by_category` calls run on the GPU (one launch
+    each instead of per-triple Python loops).  train.py itself is untouched.
 
     lazy_scores (default on): `score_fn` on the eval broadcast of train.py:146-147 returns a score-matrix HANDLE
     (blp_b200.lazy.LazyScores) that torch.cat, utils.get_metrics and the filter statement train.py:165 consume without
@@ -47,6 +48,9 @@ def patch(models_module, utils_module=None, lazy_scores=True):
     models_module.LinkPrediction.compute_loss = _m.compute_loss
     if utils_module is not None:
         utils_module.get_metrics = get_metrics
+        # train.py:173-188: the per-triple Python loops over device tensors (~10 ms per batch of 64 on a GPU) -> one launch each
+        utils_module.split_by_new_position = split_by_new_position
+        utils_module.split_by_category = split_by_category
         orig = getattr(utils_module.get_triple_filters, "__wrapped__", utils_module.get_triple_filters)
         utils_module.get_triple_filters = lazy.make_get_triple_filters(orig) if lazy_scores else orig
     lazy.enable(lazy_scores)

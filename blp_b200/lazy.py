@@ -270,19 +270,37 @@ _INDEX_CACHE = {}
 
 
 def _index_for(graph, ent2idx, num_ents, dev):
-    """One DeviceFilterIndex per (filtering graph, ent2idx, device), built on first use (utils.py:46-83 per batch in
-    the reference).  The graph must not change while it is used for filtering (train.py never changes it)."""
+    """One DeviceFilterIndex per (filtering graph, ent2idx CONTENT, device), built on first use (utils.py:46-83 per
+    batch in the reference).  The graph must not change while it is used for filtering (train.py never changes it).
+
+    ent2idx is rebuilt by every evaluation (train.py:87) and differs between the validation and the test evaluation
+    over the same graph, while a freed tensor's address is readily handed out again -- so an entry is matched by
+    OBJECT (weak reference + version counter: the per-batch calls of one evaluation, no data touched) and, for an object
+    not seen before, by comparing its content with the copy the entry was built from (once per evaluation)."""
     from .utils import DeviceFilterIndex, graph_edges
-    key = (id(graph), ent2idx.data_ptr(), int(num_ents), str(dev))
-    hit = _INDEX_CACHE.get(key)
-    if hit is not None and hit[0]() is graph:
-        return hit[1], hit[2]
+    key = (id(graph), int(num_ents), str(dev))
+    entries = _INDEX_CACHE.get(key)
+    if entries is not None and entries[0]["graph"]() is not graph:
+        entries = None                                     # a recycled id(): not the graph the entries were built for
+    if entries:
+        for e in entries:
+            if e["e2i_ref"]() is ent2idx and e["version"] == ent2idx._version:
+                return e["idx"], e["e2i_dev"]
+        host = ent2idx.detach().cpu()
+        for e in entries:
+            if e["e2i_host"].shape == host.shape and torch.equal(e["e2i_host"], host):
+                e["e2i_ref"], e["version"] = weakref.ref(ent2idx), ent2idx._version
+                return e["idx"], e["e2i_dev"]
     edges = graph_edges(graph)
     num_rel = int(edges[:, 2].max()) + 1 if len(edges) else 1
     idx = DeviceFilterIndex(edges, ent2idx, num_ents, num_rel, dev)
-    e2i = ent2idx.to(dev)
-    _INDEX_CACHE[key] = (weakref.ref(graph, lambda _r, k=key: _INDEX_CACHE.pop(k, None)), idx, e2i)
-    return idx, e2i
+    entry = {"graph": weakref.ref(graph, lambda _r, k=key: _INDEX_CACHE.pop(k, None)), "e2i_ref": weakref.ref(ent2idx),
+             "version": ent2idx._version, "e2i_host": ent2idx.detach().cpu().clone(), "idx": idx, "e2i_dev": ent2idx.to(dev)}
+    if entries is None:
+        _INDEX_CACHE[key] = entries = []
+    entries.insert(0, entry)
+    del entries[4:]                                        # validation + test (+ spare) per graph
+    return idx, entry["e2i_dev"]
 
 
 class LazyFilter(torch.Tensor):
@@ -311,8 +329,14 @@ class LazyFilter(torch.Tensor):
 
     def rows(self, dev):
         """(B, 3) int64 on the device: (head row, tail row, relation id) -- the lookup keys of the filter index."""
+        tr, e2i_host = self._triples, self._ent2idx
+        if not tr.is_cuda and torch.is_tensor(e2i_host) and not e2i_host.is_cuda:
+            # the reference's layout (train.py:87-93, 133-135: CPU triples, CPU ent2idx): map on the host, ONE small H2D
+            # copy per batch instead of a copy + two device gathers + a stack
+            tr = tr.to(torch.int64)
+            return torch.stack([e2i_host[tr[:, 0]], e2i_host[tr[:, 1]], tr[:, 2]], dim=1).to(dev)
         _, e2i = _index_for(self._graph, self._ent2idx, self._num_ents, dev)
-        tr = self._triples.to(dev)
+        tr = tr.to(dev)
         return torch.stack([e2i[tr[:, 0]], e2i[tr[:, 1]], tr[:, 2]], dim=1).contiguous()
 
     def materialize(self):

@@ -7,6 +7,7 @@ score, a loss or a rank with torch ops, and nothing falls back to the CPU.
 import contextlib
 import ctypes
 import threading
+import weakref
 
 import torch
 
@@ -222,8 +223,22 @@ def eval_rank(model, ent, h_rows, t_rows, r_rows, filt_indptr=None, filt_idx=Non
     return out
 
 
+_KV_LAST = threading.local()
+
+
 def _kvalues(k_values):
-    ks = [int(v) for v in (k_values.reshape(-1).tolist() if torch.is_tensor(k_values) else k_values)]
+    """Hit positions as a host list + ctypes array.  The reference passes ONE device tensor to every get_metrics call of
+    an evaluation (train.py:72, 153, 167); reading it back is a device synchronisation, so the last tensor OBJECT seen by
+    this thread is remembered (weak reference + version counter: an in-place change or another tensor reads again)."""
+    if torch.is_tensor(k_values):
+        last = getattr(_KV_LAST, "v", None)
+        if last is not None and last[0]() is k_values and last[1] == k_values._version:
+            ks = last[2]
+        else:
+            ks = [int(v) for v in k_values.reshape(-1).tolist()]
+            _KV_LAST.v = (weakref.ref(k_values), k_values._version, ks)
+    else:
+        ks = [int(v) for v in k_values]
     return ks, (ctypes.c_int64 * max(1, len(ks)))(*ks)
 
 

@@ -20,6 +20,44 @@ def get_metrics(pred_scores, true_idx, k_values):
     return ops.metrics_from_counts(gt, ge, k_values)
 
 
+_NEW_MASK = {}          # device -> (the new_entities object, its size when the mask was built, uint8 device mask)
+
+
+def _new_entity_mask(new_entities, dev):
+    """Membership mask of `new_entities` (a Python set of entity ids in the reference, train.py:286-296) on the device,
+    built once per set object: train.py passes the same set to every batch of an evaluation."""
+    hit = _NEW_MASK.get(dev)
+    if hit is not None and hit[0] is new_entities and hit[1] == len(new_entities):
+        return hit[2]
+    if torch.is_tensor(new_entities) and new_entities.dtype in (torch.bool, torch.uint8):
+        mask = new_entities.to(torch.uint8)
+    else:
+        ids = torch.as_tensor(sorted(int(e) for e in new_entities), dtype=torch.int64)
+        mask = torch.zeros(int(ids[-1]) + 1 if ids.numel() else 1, dtype=torch.uint8)
+        mask[ids] = 1
+    mask = mask.to(dev)
+    _NEW_MASK[dev] = (new_entities, len(new_entities), mask)     # keeps the set alive, so `is` cannot hit a recycled id
+    return mask
+
+
+def split_by_new_position(triples, mrr_values, new_entities):
+    """utils.py:114-147: the filtered MRR of one batch split by where a new entity sits (both / head only / tail only).
+    The reference walks the batch in Python with several `.item()` calls and device adds per TRIPLE (the dominant cost
+    of its eval loop on a GPU); here one launch (blp_mrr_breakdown) reads the (2B,) reciprocal ranks where they are.
+    Returns (mrr_by_position (3,), mrr_pos_counts (3,)) fp32 on mrr_values' device, like the reference."""
+    dev = ops._require_cuda(mrr_values)
+    res = ops.mrr_breakdown(mrr_values, torch.as_tensor(triples).to(dev), _new_entity_mask(new_entities, dev), None)
+    return res[0:3].to(torch.float32), res[3:6].to(torch.float32)
+
+
+def split_by_category(triples, mrr_values, rel_categories):
+    """utils.py:150-168: per relation category (1-1, 1-N, N-1, N-N) sums of the head- / tail-prediction reciprocal
+    ranks and the triple counts of one batch -> ((2, 4), (1, 4)) fp32 on mrr_values' device.  One launch."""
+    dev = ops._require_cuda(mrr_values)
+    res = ops.mrr_breakdown(mrr_values, torch.as_tensor(triples).to(dev), None, torch.as_tensor(rel_categories).to(dev))
+    return res[6:14].view(2, 4).to(torch.float32), res[14:18].view(1, 4).to(torch.float32)
+
+
 def make_ent2idx(entities, max_ent_id):
     """utils.py:31-43 (host-side index plumbing; -1 marks ids that are not candidates)."""
     idx = torch.arange(entities.shape[0])

@@ -239,3 +239,36 @@ def test_store_rows_scatters_into_row_shards(cuda_device):
     full = torch.zeros((n, d), device=cuda_device)
     blp_b200.store_rows(full, raw.to(cuda_device), rows=perm.to(cuda_device))
     assert torch.equal(full.cpu()[perm], raw)
+
+
+@pytest.mark.parametrize("b,seed", [(64, 0), (7, 1), (1, 2)])
+def test_split_by_functions_equal_the_reference(b, seed, cuda_device):
+    """utils.split_by_new_position / utils.split_by_category (utils.py:114-168) as patch() rebinds them: one launch per
+    call instead of per-triple Python loops; same (3,), (3,), (2, 4), (1, 4) fp32 tensors as the reference's own
+    functions (run here on the CPU from oracle/_ref or /root/reference) -- counts exactly, sums to fp32 rounding."""
+    from oracle import ref_loader
+    if ref_loader.available() is None:
+        pytest.skip("reference modules not built (python oracle/build_ref.py)")
+    ref_utils = ref_loader.load(("utils",))["utils"]
+    g = torch.Generator().manual_seed(seed)
+    n_ids, n_rel = 500, 11
+    triples = torch.stack([torch.randint(0, n_ids, (b,), generator=g), torch.randint(0, n_ids, (b,), generator=g),
+                           torch.randint(0, n_rel, (b,), generator=g)], dim=1)
+    recip = 1.0 / torch.randint(1, 200, (2 * b,), generator=g).float()
+    new_entities = set(torch.randint(0, n_ids, (200,), generator=g).tolist())
+    rel_categories = torch.randint(0, 4, (n_rel,), generator=g)
+    want_pos, want_cnt = ref_utils.split_by_new_position(triples, recip, new_entities)
+    want_cat, want_ccnt = ref_utils.split_by_category(triples, recip, rel_categories)
+    dev = cuda_device
+    for _ in range(2):                                       # second round: the cached membership mask
+        got_pos, got_cnt = blp_b200.split_by_new_position(triples, recip.to(dev), new_entities)
+        got_cat, got_ccnt = blp_b200.split_by_category(triples, recip.to(dev), rel_categories.to(dev))
+        assert got_pos.dtype == torch.float32 and got_pos.device.type == "cuda" and tuple(got_pos.shape) == (3,)
+        assert tuple(got_cat.shape) == (2, 4) and tuple(got_ccnt.shape) == (1, 4)
+        assert torch.equal(got_cnt.cpu(), want_cnt) and torch.equal(got_ccnt.cpu(), want_ccnt)
+        assert torch.allclose(got_pos.cpu(), want_pos, rtol=2e-6, atol=0)
+        assert torch.allclose(got_cat.cpu(), want_cat, rtol=2e-6, atol=0)
+    new_entities.add(n_ids + 5)                               # a changed set is re-read
+    t2 = torch.tensor([[n_ids + 5, 0, 0]])
+    pos, cnt = blp_b200.split_by_new_position(t2, torch.tensor([0.5, 0.25], device=dev), new_entities)
+    assert cnt.sum().item() == 1.0

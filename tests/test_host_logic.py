@@ -247,3 +247,38 @@ def test_filter_index_from_networkx_graph_as_integration_md():
                 rhf[i, ent2idx[h]] = True
     assert np.array_equal(hf, rhf) and np.array_equal(tf, rtf)
     assert rhf.sum() + rtf.sum() > 0
+
+
+def test_filter_index_cache_is_keyed_by_ent2idx_content(monkeypatch):
+    """lazy._index_for: the device filter index behind the patched utils.get_triple_filters is reused across the batches
+    of one evaluation (same ent2idx OBJECT), across evaluations whose freshly built ent2idx has the same CONTENT, and
+    rebuilt when the content differs (validation vs test entities over the same graph, train.py:87, 298-302) -- never
+    matched by a recycled address."""
+    import gc
+
+    import networkx as nx
+
+    from blp_b200 import lazy, utils as butils
+    built = []
+
+    class FakeIndex:
+        def __init__(self, edges, ent2idx, n, r, dev):
+            built.append(ent2idx.clone())
+    monkeypatch.setattr(butils, "DeviceFilterIndex", FakeIndex)
+    graph = nx.MultiDiGraph()
+    graph.add_weighted_edges_from([(0, 1, 2), (1, 2, 0)])
+    e_val = torch.arange(5)
+    i1, _ = lazy._index_for(graph, e_val, 5, "cpu")
+    assert lazy._index_for(graph, e_val, 5, "cpu")[0] is i1 and len(built) == 1          # per-batch calls: same object
+    assert lazy._index_for(graph, torch.arange(5), 5, "cpu")[0] is i1 and len(built) == 1  # next evaluation, same content
+    e_test = torch.tensor([0, 1, -1, 3, 4])
+    i2, _ = lazy._index_for(graph, e_test, 5, "cpu")
+    assert i2 is not i1 and len(built) == 2                                                # other entity set: rebuilt
+    assert lazy._index_for(graph, e_val, 5, "cpu")[0] is i1 and len(built) == 2          # both stay cached
+    e_test[2] = 2                                                                          # in-place change is noticed
+    assert lazy._index_for(graph, e_test, 5, "cpu")[0] is i1 and len(built) == 2
+    key = (id(graph), 5, "cpu")
+    assert key in lazy._INDEX_CACHE
+    del graph
+    gc.collect()
+    assert key not in lazy._INDEX_CACHE                                                    # entries die with the graph

@@ -165,6 +165,7 @@ class LazyScores(torch.Tensor):
         if self._raw is None or self._true_ptr != key:
             self._raw = self._rank(true_idx, k_values)
             self._true_ptr = key
+            self._true_keep = true_idx          # keeps the storage alive: its address cannot be handed to another tensor
         raw = self._raw
         if self._filter is None:
             return raw["recip"], raw["hits"]

@@ -69,7 +69,8 @@ def load(names=("models", "utils")):
     install_stubs()
     out = {}
     order = [n for n in ("models", "utils", "data", "train") if n in names or
-             (n in ("models", "utils", "data") and "train" in names)]
+             (n in ("models", "utils", "data") and "train" in names) or
+             (n == "models" and "utils" in names)]                      # utils.py does `import models`
     for name in order:
         if name in _cache:
             out[name] = _cache[name]

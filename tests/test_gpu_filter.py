@@ -249,7 +249,7 @@ def test_split_by_functions_equal_the_reference(b, seed, cuda_device):
     from oracle import ref_loader
     if ref_loader.available() is None:
         pytest.skip("reference modules not built (python oracle/build_ref.py)")
-    ref_utils = ref_loader.load(("utils",))["utils"]
+    ref_utils = ref_loader.load(("models", "utils"))["utils"]       # utils.py imports models
     g = torch.Generator().manual_seed(seed)
     n_ids, n_rel = 500, 11
     triples = torch.stack([torch.randint(0, n_ids, (b,), generator=g), torch.randint(0, n_ids, (b,), generator=g),

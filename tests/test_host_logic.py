@@ -282,3 +282,46 @@ def test_filter_index_cache_is_keyed_by_ent2idx_content(monkeypatch):
     del graph
     gc.collect()
     assert key not in lazy._INDEX_CACHE                                                    # entries die with the graph
+
+
+def test_k_values_readback_is_cached_per_tensor_object():
+    """ops._kvalues: the reference passes one (device) tensor to every get_metrics call of an evaluation (train.py:72);
+    it is read back once per tensor object and version, again after an in-place change or for another tensor."""
+    from blp_b200 import ops
+    k = torch.tensor([[1, 3, 10]])
+    assert ops._kvalues(k)[0] == [1, 3, 10]
+    calls = []
+    real = torch.Tensor.tolist
+
+    def counting(self):
+        calls.append(1)
+        return real(self)
+    torch.Tensor.tolist = counting
+    try:
+        assert ops._kvalues(k)[0] == [1, 3, 10] and not calls          # same object, same version: no read-back
+        k[0, 1] = 5
+        assert ops._kvalues(k)[0] == [1, 5, 10] and len(calls) == 1    # in-place change
+        assert ops._kvalues(torch.tensor([1, 10]))[0] == [1, 10] and len(calls) == 2
+        assert ops._kvalues([1, 3])[0] == [1, 3] and len(calls) == 2    # plain sequences never touch a tensor
+    finally:
+        torch.Tensor.tolist = real
+    ks, arr = ops._kvalues(())
+    assert ks == [] and len(arr) == 1
+
+
+def test_new_entity_mask_is_built_once_per_set_object():
+    """utils._new_entity_mask (behind the patched utils.split_by_new_position): one membership mask per `new_entities`
+    set object (train.py passes the same set to every batch), rebuilt when the set grows or another set arrives."""
+    from blp_b200 import utils as butils
+    dev = torch.device("cpu")
+    s = {3, 7, 11}
+    m1 = butils._new_entity_mask(s, dev)
+    assert m1.dtype == torch.uint8 and m1.tolist() == [0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1]
+    assert butils._new_entity_mask(s, dev) is m1
+    s.add(1)
+    m2 = butils._new_entity_mask(s, dev)
+    assert m2 is not m1 and m2[1] == 1
+    assert butils._new_entity_mask({3, 7, 11, 1}, dev) is not m2           # an equal but different object is re-read
+    assert butils._new_entity_mask(set(), dev).tolist() == [0]
+    mask = torch.tensor([True, False, True])
+    assert butils._new_entity_mask(mask, dev).tolist() == [1, 0, 1]

@@ -241,6 +241,33 @@ def test_store_rows_scatters_into_row_shards(cuda_device):
     assert torch.equal(full.cpu()[perm], raw)
 
 
+@pytest.mark.parametrize("normalize", (True, False))
+def test_store_rows_stream_path(normalize, cuda_device):
+    """Bulk table production (>= 4,096 contiguous rows of d = 128): the persistent TMA pipeline (store_rows_stream_kernel:
+    bulk loads -> in-place normalisation in shared memory -> bulk stores).  Bit-equal to F.normalize's CPU bits (the
+    oracle restatement pinned on the reference's encode()), ragged last tile, zero / tiny rows, and row-sharded
+    destinations clipped on the host (rows owned by other ranks are neither read nor written)."""
+    from oracle import np_oracle
+    n, d = 40003, 128
+    g = torch.Generator().manual_seed(12)
+    raw = torch.randn(n, d, generator=g)
+    raw[5] = 0.0
+    raw[77] *= 1e-30
+    raw[40002] *= 1e20
+    want = torch.from_numpy(np_oracle.l2_normalize_rows(raw.numpy())) if normalize else raw
+    x = raw.to(cuda_device)
+    full = torch.full((n, d), float("nan"), device=cuda_device)
+    blp_b200.store_rows(full, x, normalize=normalize)
+    assert torch.equal(full.cpu(), want)
+    # three row shards, encoder batches of 8,192 rows handed to every rank (train.py:95-123)
+    for rank in range(3):
+        lo, hi = blp_b200.shard_bounds(n, 3, rank)
+        shard = torch.full((hi - lo, d), float("nan"), device=cuda_device)
+        for idx in range(0, n, 8192):
+            blp_b200.store_rows(shard, x[idx:idx + 8192], row0=idx, normalize=normalize, ent_offset=lo)
+        assert torch.equal(shard.cpu(), want[lo:hi]), rank
+
+
 @pytest.mark.parametrize("b,seed", [(64, 0), (7, 1), (1, 2)])
 def test_split_by_functions_equal_the_reference(b, seed, cuda_device):
     """utils.split_by_new_position / utils.split_by_category (utils.py:114-168) as patch() rebinds them: one launch per

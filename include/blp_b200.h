@@ -364,7 +364,7 @@ int blp_negative_sample(int64_t batch, int64_t num_neg, int64_t repeats, uint64_
  * [ent_offset, ent_offset + n_local) are skipped, so every rank can be handed the same encoder batch
  * and keeps only what it owns.  normalize != 0: x / max(||x||_2, 1e-12) in ATen's CPU order (bit-equal).
  * d == 128, dst_rows == NULL and m >= 4096 (bulk table production): a persistent TMA pipeline (bulk loads, in-place
- * normalisation in shared memory, bulk stores) at ~0.91 of the HBM copy peak; emb may alias the destination rows. */
+ * normalisation in shared memory, bulk stores) at ~0.91 of the HBM copy peak. */
 int blp_store_rows(const float *emb, int64_t m, int d, int normalize, const int64_t *dst_rows, int64_t row0,
                    float *ent_shard, int64_t n_local, int64_t ent_offset, void *stream);
 

@@ -16,7 +16,8 @@ from . import _lib, lazy, ops  # noqa: F401
 from .ops import store_rows  # noqa: F401
 from ._lib import BlpError  # noqa: F401
 from .graphs import GraphedLossStep  # noqa: F401
-from .evaluate import AlignedTriples, RankSweepPlan, breakdowns, finalize, gather_rows, rank_sweep, shard_bounds  # noqa: F401
+from .evaluate import (AlignedTriples, RankSweepPlan, breakdowns, finalize, gather_rows, rank_sweep, shard_bounds,  # noqa: F401
+                       topk_sweep)  # noqa: F401
 from .models import (InductiveLinkPrediction, LinkPrediction, TransductiveLinkPrediction,  # noqa: F401
                      complex_score, compute_loss, distmult_score, fused_compute_loss, l2_regularization,
                      margin_loss, nll_loss, simple_score, transe_score)

@@ -533,6 +533,62 @@ def breakdowns(out, triples_ids, new_entities=None, rel_categories=None, max_ent
             "mrr_cat_count": res[14:18].view(1, 4)}
 
 
+def topk_sweep(rel_model, ent_emb, rel_weight, triples, k=10, *, ent_offset=0, group=None, h_rows=None, t_rows=None,
+               chunk=128, score_fn=None):
+    """The k best-scoring candidate entities of every head- and tail-prediction query (the predictions behind the
+    ranks of train.py:146-153), for a table that may be row-sharded over `group`.
+
+    Every rank scores its own rows with the exact score kernels (score_fn(ent (1, N_local, D), tails, rels) /
+    score_fn(heads, ent, rels): the reference's bits), keeps its k best per query, and ONE all-gather of the packed
+    (score bits, global row) pairs -- 16 * k bytes per query and rank -- lets every rank merge the per-shard lists.
+    Order: score descending, ties by ascending global row (a stable sort per shard, shards concatenated in rank
+    order), so the result is bit-identical for any number of shards.
+
+    triples (T, 3) int64 (head row, tail row, rel id) as for rank_sweep; h_rows / t_rows optional pre-gathered true
+    rows.  Returns dict(scores (2, T, k) f32, index (2, T, k) int64 global rows; [0] = head prediction, [1] = tail
+    prediction); slots beyond the number of candidates hold -inf / -1.  `score_fn` is a test seam (CPU stand-in for the
+    score kernels in the gloo tests).
+    """
+    dev = ent_emb.device
+    triples = triples.to(dev).reshape(-1, 3)
+    T, k = triples.shape[0], int(k)
+    if k <= 0:
+        raise ValueError("k must be positive")
+    world, rank = _world(group)
+    n_local, d = ent_emb.shape
+    if score_fn is None:
+        def score_fn(heads, tails, rels):
+            return ops.score(rel_model, heads, tails, rels)
+    rel_rows = rel_weight.detach().index_select(0, triples[:, 2])
+    if h_rows is None:
+        h_rows = gather_rows(ent_emb, ent_offset, triples[:, 0], group)
+    if t_rows is None:
+        t_rows = gather_rows(ent_emb, ent_offset, triples[:, 1], group)
+    kk = min(k, n_local)
+    vals = torch.full((2, T, k), float("-inf"), dtype=torch.float32, device=dev)
+    idx = torch.full((2, T, k), -1, dtype=torch.int64, device=dev)
+    ent3 = ent_emb.unsqueeze(0)
+    for lo in range(0, T, max(1, int(chunk))):
+        hi = min(T, lo + max(1, int(chunk)))
+        if kk == 0:
+            break
+        r = rel_rows[lo:hi].unsqueeze(1)
+        for role, pred in ((0, score_fn(ent3, t_rows[lo:hi].unsqueeze(1), r)), (1, score_fn(h_rows[lo:hi].unsqueeze(1), ent3, r))):
+            sv, si = torch.sort(pred, dim=1, descending=True, stable=True)     # ties: lower row first
+            vals[role, lo:hi, :kk] = sv[:, :kk]
+            idx[role, lo:hi, :kk] = si[:, :kk] + ent_offset
+    if world > 1:
+        # one collective: (score bits, global row) packed as int64 pairs, gathered from every shard
+        packed = torch.stack([vals.view(torch.int32).to(torch.int64), idx], dim=-1).contiguous()
+        parts = [torch.empty_like(packed) for _ in range(world)]
+        _dist().all_gather(parts, packed, group=group)
+        allv = torch.cat([p[..., 0].to(torch.int32).view(torch.float32) for p in parts], dim=-1)   # rank order = row order
+        alli = torch.cat([p[..., 1] for p in parts], dim=-1)
+        sv, order = torch.sort(allv, dim=-1, descending=True, stable=True)
+        vals, idx = sv[..., :k].contiguous(), alli.gather(-1, order)[..., :k].contiguous()
+    return {"scores": vals, "index": idx}
+
+
 def finalize(out, num_queries=None):
     """Host-side normalisation (train.py:196-200): one D2H read of the fp64 accumulators per sweep."""
     res = {}

@@ -285,3 +285,30 @@ def test_wide_transe_sweep_vs_oracle(d, n, b, cuda_device):
     a = blp_b200.rank_sweep("transe", e[:cut].contiguous(), r, triples, h_rows=h_rows, t_rows=t_rows)
     c = blp_b200.rank_sweep("transe", e[cut:].contiguous(), r, triples, ent_offset=cut, h_rows=h_rows, t_rows=t_rows)
     assert torch.equal(a["gt"] + c["gt"], out["gt"]) and torch.equal(a["ge"] + c["ge"], out["ge"])
+
+
+@pytest.mark.parametrize("model", ("transe", "distmult", "complex", "simple"))
+def test_topk_sweep_matches_the_oracle_scores(model, cuda_device):
+    """blp_b200.topk_sweep: the k best candidates per query are the head of the stable descending sort of the oracle's
+    full score rows (train.py:146-147 bits), rows as global ids; the true entity's rank from rank_sweep is consistent
+    with its position in the list."""
+    n, t, k = 700, 20, 10
+    ent, rel, heads, tails, rels = make_inputs(model, n, 128, t, seed=17, n_rel=7)
+    dev = cuda_device
+    triples = torch.stack([heads, tails, rels], dim=1).to(dev)
+    out = blp_b200.topk_sweep(model, ent.to(dev), rel.to(dev), triples, k=k, chunk=8)
+    co = c_oracle.eval_rank(model, ent.numpy(), ent[heads].numpy(), ent[tails].numpy(), rel[rels].numpy(), heads.numpy(),
+                            tails.numpy(), want_scores=True)
+    scores = torch.from_numpy(np.asarray(co["scores"])).reshape(2, t, n)
+    for role in range(2):
+        sv, si = torch.sort(scores[role], dim=1, descending=True, stable=True)
+        assert torch.equal(out["scores"][role].cpu(), sv[:, :k])
+        assert torch.equal(out["index"][role].cpu(), si[:, :k])
+    ranks = blp_b200.rank_sweep(model, ent.to(dev), rel.to(dev), triples)
+    true = torch.stack([heads, tails]).to(dev)
+    hit = out["index"] == true.unsqueeze(-1)
+    in_list, pos = hit.any(-1), hit.to(torch.int64).argmax(-1)
+    untied = (ranks["ge"] - ranks["gt"]) == 1                  # no other candidate shares the true score
+    assert torch.equal(in_list[untied], (ranks["gt"] < k)[untied])          # in the list <=> fewer than k strictly better
+    sel = untied & in_list
+    assert torch.equal(pos[sel], ranks["gt"][sel].to(torch.int64))          # ... at position = number of better candidates

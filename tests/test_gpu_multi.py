@@ -115,3 +115,38 @@ def test_dataparallel_threads_compute_loss_concurrently(model, loss, cuda_device
         np.add.at(want_grad_rel, rels[sl, 0].numpy(), co["grad_rel"].astype(np.float64) / n_dev)
     got = m.rel_emb.weight.grad.cpu().numpy()
     assert np.abs(got - want_grad_rel).max() <= 2e-5 * np.abs(want_grad_rel).max()
+
+
+def _topk_worker(rank, world, port, model, k, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g, ent2idx, rows = _inputs(model)
+        table = torch.from_numpy(g["ent_emb"])
+        lo, hi = blp_b200.shard_bounds(table.shape[0], world, rank)
+        out = blp_b200.topk_sweep(model, table[lo:hi].contiguous().to(dev), torch.from_numpy(g["rel_weight"]).to(dev), rows.to(dev),
+                                  k=k, ent_offset=lo, group=dist.group.WORLD, chunk=16)
+        if rank == 0:
+            ret.update(scores=out["scores"].cpu().numpy(), index=out["index"].cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", ("transe", "complex"))
+def test_nccl_sharded_topk_equals_single_gpu(model, cuda_device):
+    """topk_sweep over row shards: per-shard top-k, ONE NCCL all-gather of the packed (score bits, row) pairs, merge --
+    the same scores and rows as the single-GPU list, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    g, ent2idx, rows = _inputs(model)
+    ent, rel = torch.from_numpy(g["ent_emb"]).to(cuda_device), torch.from_numpy(g["rel_weight"]).to(cuda_device)
+    single = blp_b200.topk_sweep(model, ent, rel, rows.to(cuda_device), k=10)
+    ret = mp.Manager().dict()
+    mp.spawn(_topk_worker, args=(world, _free_port(), model, 10, ret), nprocs=world, join=True)
+    assert np.array_equal(ret["scores"], single["scores"].cpu().numpy())
+    assert np.array_equal(ret["index"], single["index"].cpu().numpy())

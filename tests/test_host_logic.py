@@ -325,3 +325,62 @@ def test_new_entity_mask_is_built_once_per_set_object():
     assert butils._new_entity_mask(set(), dev).tolist() == [0]
     mask = torch.tensor([True, False, True])
     assert butils._new_entity_mask(mask, dev).tolist() == [1, 0, 1]
+
+
+def _np_score_fn(model):
+    """CPU stand-in for the score kernels (test seam of topk_sweep): the NumPy restatement of models.py:222-248."""
+    fn = getattr(np_oracle, model + "_score")
+
+    def score(heads, tails, rels):
+        return torch.from_numpy(np.asarray(fn(heads.numpy(), tails.numpy(), rels.numpy()), dtype=np.float32))
+    return score
+
+
+def _topk_inputs(model, n=97, t=11, n_rel=5, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    ent = torch.randn(n, 16, generator=g)
+    ent[40] = ent[7]                                   # tied candidates in different shards: order must be by row
+    ent[96] = ent[7]
+    rel = torch.randn(n_rel, 16, generator=g) * 0.3
+    triples = torch.stack([torch.randint(0, n, (t,), generator=g), torch.randint(0, n, (t,), generator=g),
+                           torch.randint(0, n_rel, (t,), generator=g)], dim=1)
+    return ent, rel, triples
+
+
+def _topk_worker(rank, world, port, model, k, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ent, rel, triples = _topk_inputs(model)
+        lo, hi = shard_bounds(ent.shape[0], world, rank)
+        out = blp_b200.topk_sweep(model, ent[lo:hi].contiguous(), rel, triples, k=k, ent_offset=lo, group=dist.group.WORLD,
+                                  chunk=4, score_fn=_np_score_fn(model))
+        ret[rank] = (out["scores"].numpy(), out["index"].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", ("transe", "distmult"))
+@pytest.mark.parametrize("world,k", ((2, 10), (3, 40)))
+def test_topk_sweep_sharded_equals_single_rank_gloo(model, world, k):
+    """topk_sweep: per-shard top-k + ONE all-gather + merge gives the single-rank list bit for bit (scores and rows,
+    ties by ascending row), also when k exceeds a shard's row count; and the single-rank list is the stable descending
+    sort of the full score rows."""
+    import torch.multiprocessing as mp
+    ent, rel, triples = _topk_inputs(model)
+    single = blp_b200.topk_sweep(model, ent, rel, triples, k=k, score_fn=_np_score_fn(model))
+    fn = _np_score_fn(model)
+    r = rel[triples[:, 2]].unsqueeze(1)
+    full = (fn(ent.unsqueeze(0), ent[triples[:, 1]].unsqueeze(1), r), fn(ent[triples[:, 0]].unsqueeze(1), ent.unsqueeze(0), r))
+    for role in range(2):
+        sv, si = torch.sort(full[role], dim=1, descending=True, stable=True)
+        assert torch.equal(single["scores"][role], sv[:, :k]) and torch.equal(single["index"][role], si[:, :k])
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_topk_worker, args=(world, _free_port(), model, k, ret), nprocs=world, join=True)
+    for rank in range(world):
+        assert np.array_equal(ret[rank][0], single["scores"].numpy()), rank
+        assert np.array_equal(ret[rank][1], single["index"].numpy()), rank
+    few = blp_b200.topk_sweep(model, ent[:3].contiguous(), rel, triples % 3, k=5, score_fn=_np_score_fn(model))
+    assert bool((few["index"][..., 3:] == -1).all()) and bool(torch.isinf(few["scores"][..., 3:]).all())

@@ -710,6 +710,24 @@ def config_legs(args, dev, peaks, fp32_peak, hbm_peak):
         legs[f"train_transe_b{b}_k{k}"] = {
             "config": f"compute_loss forward + backward, BLP-transe dim=128, B={b}, K={k}, margin loss (one fused launch)",
             "us_per_step_kernels": us, "triples_per_s": b * (k + 1) / (us * 1e-6), "roofline": roof}
+
+    # entity-table production (F.normalize + the write into a row shard, train.py:95-123, models.py:38-43):
+    # a pure stream, 2 * N * D * 4 bytes, against the measured HBM copy peak
+    for rows in (600000, 4800000):
+        try:
+            raw = torch.randn(rows, 128, device=dev)
+            shard = torch.empty_like(raw)
+            ms = time_calls(lambda: blp_b200.store_rows(shard, raw, normalize=True), reps=10, warm=3)
+            nbytes = 2 * rows * 512
+            legs[f"store_rows_{rows}"] = {
+                "config": f"blp_store_rows: L2-normalise (ATen order, bit-equal) + store {rows} rows of dim=128 into a row shard",
+                "ms_per_call": ms,
+                "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": nbytes}}
+            del raw, shard
+        except Exception as exc:
+            legs[f"store_rows_{rows}"] = {"error": str(exc)[:160]}
+    torch.cuda.empty_cache()
     return legs
 
 
@@ -1025,7 +1043,7 @@ def main_b200(args):
                         ("wn18rr_complex_fast", "complex_fast"), ("wn18rr_complex_exact", "complex_exact"),
                         ("fb15k237_transe_eval_batch_64", "transe_e64"), ("fb15k237_transe_eval_batch_64_overlapped", "transe_e64_overlapped"),
                         ("fb15k237_transe_d768", "transe_d768"),
-                        ("train_transe_b1024_k512", "train_b1024")):
+                        ("train_transe_b1024_k512", "train_b1024"), ("store_rows_4800000", "store_rows_4p8m")):
             r = legs.get(nm, {}).get("roofline")
             if r:
                 roofline[tag + "_bound"] = r["bound"]
